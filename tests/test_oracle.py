@@ -1,0 +1,111 @@
+"""Pin the oracles (torch restatement + plain C) against the reference-generated goldens
+and against analytic known-answer tests.  CPU only."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden_names, load_golden, max_abs_rel, rel_l2
+from oracle import spectre_mix_oracle as oracle
+
+MIX_CASES = golden_names("mix_")
+
+
+def _t(x):
+    return None if x is None else torch.from_numpy(x)
+
+
+@pytest.mark.parametrize("name", MIX_CASES)
+def test_torch_oracle_matches_reference_goldens(name):
+    g = load_golden(name)
+    n_fft, H, dg = int(g["n_fft"]), int(g["num_heads"]), int(g["group_width"])
+    mem = _t(g.get("mem"))
+    y_loop = oracle.mix_head_loop(_t(g["V"]), _t(g["gate"]), n_fft, H, mem).numpy()
+    y_flat = oracle.mix_flat(_t(g["V"]), _t(g["gate"]), n_fft, dg, mem).numpy()
+    # same library, same call sites: the head loop must reproduce the reference bit for bit
+    assert np.array_equal(y_loop, g["out"])
+    assert rel_l2(y_flat, g["out"]) < 1e-6 and max_abs_rel(y_flat, g["out"]) < 1e-5
+
+
+@pytest.mark.parametrize("name", MIX_CASES)
+def test_c_oracle_matches_reference_goldens(name, c_oracle):
+    g = load_golden(name)
+    y = c_oracle(g["V"], g["gate"], g.get("mem"), int(g["n_fft"]), int(g["group_width"]))
+    assert y.shape == g["out"].shape
+    # C oracle computes in double; the golden is the reference's fp32 (MKL) result
+    assert rel_l2(y, g["out"]) < 2e-6 and max_abs_rel(y, g["out"]) < 1e-5
+
+
+def test_c_oracle_matches_fp64_torch(c_oracle):
+    torch.manual_seed(0)
+    V = torch.randn(2, 50, 12)
+    gate = torch.randn(2, 3, 33, dtype=torch.cfloat)
+    mem = torch.randn(33, 12, dtype=torch.cfloat)
+    y64 = oracle.mix_flat(V, gate, 64, 4, mem, dtype=torch.float64).numpy()
+    y = c_oracle(V.numpy(), gate.numpy(), mem.numpy(), 64, 4)
+    assert rel_l2(y, y64) < 2e-7
+    # non power of two transform length goes through the O(n^2) definition
+    gate2 = torch.randn(2, 3, 31, dtype=torch.cfloat)
+    y64 = oracle.mix_flat(V, gate2, 60, 4, None, dtype=torch.float64).numpy()
+    y = c_oracle(V.numpy(), gate2.numpy(), None, 60, 4)
+    assert rel_l2(y, y64) < 2e-7
+
+
+def test_truncation_when_N_exceeds_n_fft(c_oracle):
+    # spectre.py:506 truncates to n_fft rows and the output shrinks
+    torch.manual_seed(1)
+    V = torch.randn(1, 40, 4)
+    gate = torch.randn(1, 1, 17, dtype=torch.cfloat)
+    y = oracle.mix_flat(V, gate, 32, 4)
+    assert y.shape == (1, 32, 4)
+    yc = c_oracle(V.numpy(), gate.numpy(), None, 32, 4)
+    assert rel_l2(yc, y.numpy()) < 2e-6
+
+
+# ---------------- analytic known-answer tests (no reference needed) ----------------
+@pytest.mark.parametrize("n_fft,N", [(64, 64), (64, 40), (256, 256)])
+def test_kat_identity_gate(n_fft, N, c_oracle):
+    torch.manual_seed(2)
+    V = torch.randn(2, N, 8)
+    gate = torch.ones(2, 2, n_fft // 2 + 1, dtype=torch.cfloat)
+    for y in (oracle.mix_flat(V, gate, n_fft, 4).numpy(), c_oracle(V.numpy(), gate.numpy(), None, n_fft, 4)):
+        assert max_abs_rel(y, V.numpy()) < 1e-5
+
+
+def test_kat_shift_gate(c_oracle):
+    # gate[k] = exp(-2 pi i k s / n) is a circular shift by s (linear when N + s <= n_fft)
+    n_fft, s, N = 128, 5, 100
+    k = torch.arange(n_fft // 2 + 1)
+    gate = torch.exp(-2j * torch.pi * k * s / n_fft).to(torch.cfloat).expand(1, 1, -1).contiguous()
+    torch.manual_seed(3)
+    V = torch.randn(1, N, 4)
+    want = torch.zeros(1, N, 4)
+    want[:, s:] = V[:, : N - s]
+    for y in (oracle.mix_flat(V, gate, n_fft, 4).numpy(), c_oracle(V.numpy(), gate.numpy(), None, n_fft, 4)):
+        assert np.abs(y - want.numpy()).max() < 1e-5
+
+
+def test_kat_dc_nyquist_imag_ignored_and_memory_only():
+    torch.manual_seed(4)
+    n_fft = 64
+    V = torch.randn(2, 64, 8)
+    gate = torch.randn(2, 2, 33, dtype=torch.cfloat)
+    mem = torch.randn(33, 8, dtype=torch.cfloat)
+    y0 = oracle.mix_flat(V, gate, n_fft, 4, mem)
+    # zero gate: every batch row is irfft(memory)
+    yz = oracle.mix_flat(V, torch.zeros_like(gate), n_fft, 4, mem)
+    want = torch.fft.irfft(mem, n=n_fft, dim=0)
+    assert torch.allclose(yz[0], want, atol=1e-6) and torch.allclose(yz[1], want, atol=1e-6)
+    # imag of memory's bin 0 and bin n/2 has no effect
+    mem2 = mem.clone()
+    mem2[0] = torch.complex(mem[0].real, torch.randn(8))
+    mem2[-1] = torch.complex(mem[-1].real, torch.randn(8))
+    assert torch.equal(oracle.mix_flat(V, gate, n_fft, 4, mem2), y0)
+
+
+def test_decode_restatements_match_reference_goldens():
+    g = load_golden("decode_prefill_n256_d32")
+    spec = oracle.prefill_spectrum(_t(g["V"]), 256).numpy()
+    assert np.array_equal(spec, g["prefix_fft"])
+    for p, want in zip(g["pruned_pos"], g["pruned"]):
+        got = oracle.pruned_irfft_single(_t(g["X_half"]), 256, int(p)).numpy()
+        assert np.allclose(got, want, rtol=1e-5, atol=1e-6)
