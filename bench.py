@@ -1,0 +1,318 @@
+#!/usr/bin/env python
+"""bench.py -- Spectre spectral-mix forward throughput on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one pass of the hot path (rfft -> gate multiply -> irfft, all 12 heads / 48 gate groups in
+one kernel launch) over one per-GPU batch of synthetic (B, 4096, 768) fp32 tokens.  The batch dimension
+is the only thing sharded: every rank owns B rows, no data-path collective exists (weak scaling);
+NCCL carries the barriers and the max/sum reductions of the timing.
+
+Rank 0 prints ONE JSON line: value = whole-job tokens/s with inputs resident in HBM; `roofline` = the
+kernel's algorithmic bytes (6336.1 B/token) / CUDA-event launch time against the measured
+copy bandwidth in MEASURED_PEAKS.json; `e2e` = the same metric through the host-buffer C-ABI entry
+(spectre_mix_fwd_host: pinned host memory -> H2D -> kernel -> D2H inside the timed region);
+`cpu_baseline` = the reference's CPU path (torch.fft head loop restated in oracle/) timed on this
+box's host cores on a bounded sample.  `--impl reference` times only that CPU path.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+SEQ, D_MODEL, HEADS, GROUPS = 4096, 768, 12, 4
+D_G = D_MODEL // HEADS // GROUPS          # 16 channels per gate group
+NG = HEADS * GROUPS                       # 48 gate rows per batch row
+F_HALF = SEQ // 2 + 1
+METRIC = "Spectre-block fwd tokens/sec at seq=4096 d=768; achieved HBM GB/s vs peak"
+UNIT = "tokens/s"
+
+
+def algorithmic_bytes(B: int, es: int = 4) -> int:
+    """V in + out + gate, per call."""
+    return B * SEQ * D_MODEL * es * 2 + B * NG * F_HALF * 8
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (of measured)"
+        except Exception:
+            pass
+    return 6650.0, "B200_PROFILING.md fallback 6.65 TB/s (of fallback)"
+
+
+def ncu_traffic_per_token():
+    """dram bytes per token from the committed ncu capture (profiles/roofline_traffic.json), or None."""
+    p = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["dram_bytes_per_token"])
+        except Exception:
+            return None
+    return None
+
+
+class ClockSampler:
+    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index: int, period_s: float = 0.004):
+        self.period, self.samples, self.reasons, self.max_mhz = period_s, [], set(), None
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    _NAMES = {0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown",
+              0x10: "sync_boost", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+              0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting"}
+
+    def _run(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(
+                    nv, "nvmlDeviceGetCurrentClocksEventReasons") else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in self._NAMES.items():
+                    if mask & bit and name != "gpu_idle":
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def __enter__(self):
+        if self.nv is not None:
+            self._thr = threading.Thread(target=self._run, daemon=True)
+            self._thr.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self._thr is not None:
+            self._thr.join()
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": 0}
+        return {"sm_mhz": statistics.median(self.samples), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def cpu_reference_path(torch, batch: int, min_seconds: float, max_reps: int):
+    """The reference's CPU path (spectre.py:506, :542-553 looped over heads as :712-713) on host cores."""
+    from oracle import spectre_mix_oracle as oracle
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    gen = torch.Generator().manual_seed(0)
+    V = torch.randn(batch, SEQ, D_MODEL, generator=gen)
+    gate = torch.randn(batch, NG, F_HALF, dtype=torch.cfloat, generator=gen)
+    with torch.no_grad():
+        oracle.mix_head_loop(V, gate, SEQ, HEADS)          # warm-up (MKL plan creation)
+        times = []
+        t_all = time.perf_counter()
+        while len(times) < max_reps and (time.perf_counter() - t_all < min_seconds or len(times) < 3):
+            t0 = time.perf_counter()
+            oracle.mix_head_loop(V, gate, SEQ, HEADS)
+            times.append(time.perf_counter() - t0)
+    return {"tokens": batch * SEQ, "times": times, "threads": torch.get_num_threads()}
+
+
+def run_reference(args):
+    """--impl reference: the CPU implementation of the path, all host threads, bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import torch
+    from oracle import spectre_mix_oracle as oracle
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    batch = 8
+    gen = torch.Generator().manual_seed(0)
+    V = torch.randn(batch, SEQ, D_MODEL, generator=gen)
+    gate = torch.randn(batch, NG, F_HALF, dtype=torch.cfloat, generator=gen)
+    with torch.no_grad():
+        for _ in range(max(args.warmup, 1)):
+            oracle.mix_head_loop(V, gate, SEQ, HEADS)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            oracle.mix_head_loop(V, gate, SEQ, HEADS)
+        dt = time.perf_counter() - t0
+    value = batch * SEQ * args.steps / dt
+    sample = f"B={batch} rows of seq={SEQ} d={D_MODEL} fp32 per step (CPU throughput is batch-insensitive, SURVEY section 6)"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"reference CPU path: torch.fft rfft -> gate -> irfft looped over {HEADS} heads "
+                               f"(oracle port of spectre.py:506,542-553,712-718), seq={SEQ} d={D_MODEL}",
+                   "seq_len": SEQ, "d_model": D_MODEL, "heads": HEADS, "gate_groups": NG, "batch_per_step": batch},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=256, help="batch rows per GPU per step (device-resident leg)")
+    ap.add_argument("--e2e-batch", type=int, default=32, help="batch rows per GPU per step (host-buffer leg)")
+    ap.add_argument("--e2e-steps", type=int, default=6)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import fft_b200
+    from fft_b200 import _lib
+    _lib.load()  # fail loudly when the CUDA library is missing: there is no fallback
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    assert torch.cuda.is_available(), "bench.py (ours) needs a CUDA device"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    B = args.batch
+    gen = torch.Generator(device=dev).manual_seed(rank)
+    # two input/output sets, each far larger than the 126 MB L2 (B=256: 3.2 GB per tensor), alternated per step
+    nsets = 2
+    Vs = [torch.randn(B, SEQ, D_MODEL, device=dev, generator=gen) for _ in range(nsets)]
+    gates = [torch.randn(B, NG, F_HALF, dtype=torch.cfloat, device=dev, generator=gen) for _ in range(nsets)]
+    lib = _lib.load()
+    outs = [torch.empty(B, SEQ, D_MODEL, device=dev) for _ in range(nsets)]
+    stream = torch.cuda.current_stream(dev)
+
+    import ctypes
+
+    def launch(i):
+        V, g, o = Vs[i % nsets], gates[i % nsets], outs[i % nsets]
+        rc = lib.spectre_mix_fwd(V.data_ptr(), 0, V.stride(0), V.stride(1), g.data_ptr(), None, 0, o.data_ptr(), 0,
+                                 o.stride(0), o.stride(1), B, SEQ, SEQ, D_MODEL, D_G, ctypes.c_void_p(stream.cuda_stream))
+        _lib.check(rc, "spectre_mix_fwd")
+
+    for i in range(args.warmup):
+        launch(i)
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clk:
+        barrier()
+        ev0.record(stream)
+        for i in range(args.steps):
+            launch(i)
+        ev1.record(stream)
+        barrier()
+    elapsed_ms = ev0.elapsed_time(ev1)
+    checksum = outs[0].double().sum()
+    t = torch.tensor([elapsed_ms], device=dev, dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(checksum, op=dist.ReduceOp.SUM)
+    elapsed_ms = float(t.item())
+    tokens_per_step = B * SEQ * world
+    value = tokens_per_step * args.steps / (elapsed_ms * 1e-3)
+    ms_per_step = elapsed_ms / args.steps
+
+    # roofline of the (only) kernel: one launch per step per GPU
+    peak, peak_src = measured_peak()
+    achieved = algorithmic_bytes(B) / (ms_per_step * 1e-3) / 1e9
+    tpt = ncu_traffic_per_token()
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None if tpt is None else tpt * B * SEQ, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": algorithmic_bytes(B), "kernel": "spx::spectre_mix_kernel"}
+
+    # ---- e2e: host buffers through the C-ABI host entry (H2D + kernel + D2H inside the timed region)
+    Be = args.e2e_batch
+    hV = torch.randn(Be, SEQ, D_MODEL, generator=torch.Generator().manual_seed(100 + rank)).pin_memory()
+    hg = torch.randn(Be, NG, F_HALF, dtype=torch.cfloat, generator=torch.Generator().manual_seed(200 + rank)).pin_memory()
+    ho = torch.empty(Be, SEQ, D_MODEL).pin_memory()
+    for _ in range(2):
+        fft_b200.spectral_mix_host(hV, hg, n_fft=SEQ, group_width=D_G, out=ho)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.e2e_steps):
+        fft_b200.spectral_mix_host(hV, hg, n_fft=SEQ, group_width=D_G, out=ho)
+        _ = float(ho[0, 0, 0])  # the step's result is read on the host
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = Be * SEQ * world * args.e2e_steps / float(te.item())
+    e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(hV.numel() * 4 + hg.numel() * 8),
+           "d2h_bytes_per_step": int(ho.numel() * 4), "batch_per_gpu": Be, "steps": args.e2e_steps,
+           "entry": "spectre_mix_fwd_host (C ABI, pinned host buffers, chunked H2D/kernel/D2H on 2 streams)"}
+
+    # ---- CPU baseline beside it (rank 0 at N=1 only)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        r = cpu_reference_path(torch, batch=8, min_seconds=args.cpu_seconds, max_reps=200)
+        best = min(r["times"])
+        cpu = {"value": r["tokens"] / statistics.median(r["times"]), "unit": UNIT, "cores": r["threads"], "kind": "port",
+               "sample": f"B=8 rows of seq={SEQ} d={D_MODEL} fp32, {len(r['times'])} reps after 1 warm-up, median "
+                         f"(best {r['tokens'] / best:.3e}); oracle/spectre_mix_oracle.py mix_head_loop = spectre.py:506,"
+                         f"542-553 looped over {HEADS} heads as :712-718"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"fused rFFT->gate->irFFT kernel (all {HEADS} heads / {NG} gate groups per launch), "
+                                   f"batch={B}/GPU seq={SEQ} d={D_MODEL} fp32, no spectral memory",
+                       "global_batch": B * world, "batch_per_gpu": B, "seq_len": SEQ, "d_model": D_MODEL, "heads": HEADS,
+                       "gate_groups": NG, "parallelism": f"batch-shard x{world} (no data-path collective)",
+                       "l2": f"inputs larger than L2: {B * SEQ * D_MODEL * 4 / 1e6:.0f} MB per tensor, {nsets} buffer sets alternated",
+                       "plan": fft_b200.plan_info(B, SEQ, SEQ, D_MODEL, D_G)},
+            "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu, "clocks": clk.summary(),
+            "gpu_launches": args.steps * world, "checksum": float(checksum.item()),
+        }
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,88 @@
+"""ctypes binding of the C ABI declared in ``include/spectre_mix.h``.
+
+The library is built in-tree (``fft_b200/_C/libspectre_mix.so``) by
+``__graft_entry__.build()`` / ``make -C fft_b200/csrc``.  Loading is lazy and LOUD: a
+missing library raises ``RuntimeError`` -- there is no fallback path.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_C", "libspectre_mix.so")
+
+F32, BF16 = 0, 1
+
+# every symbol include/spectre_mix.h declares (checked by tests/test_abi.py)
+SYMBOLS = (
+    "spectre_mix_abi_version",
+    "spectre_mix_last_error",
+    "spectre_mix_fwd",
+    "spectre_mix_fwd_host",
+    "spectre_rfft_fwd",
+    "spectre_mix_plan",
+    "spectre_mix_set_tile_channels",
+    "spectre_mix_set_prefetch",
+)
+
+
+class PlanInfo(ctypes.Structure):
+    _fields_ = [
+        ("n_fft", ctypes.c_int),
+        ("radix", ctypes.c_int * 4),
+        ("tile_channels", ctypes.c_int),
+        ("threads", ctypes.c_int),
+        ("ctas_per_sm", ctypes.c_int),
+        ("smem_bytes", ctypes.c_int),
+        ("grid", ctypes.c_int),
+        ("launches", ctypes.c_int),
+        ("algorithmic_bytes", ctypes.c_int64),
+    ]
+
+
+_lib = None
+_lock = threading.Lock()
+
+
+def load():
+    """Return the loaded library; raise if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"fft_b200: CUDA library not built: {LIB_PATH} is missing. "
+                "Run `python -c 'import __graft_entry__ as g; g.build()'` or `make -C fft_b200/csrc`. "
+                "There is no CPU fallback for the spectral-mix path."
+            )
+        lib = ctypes.CDLL(LIB_PATH)
+        vp, i32, i64 = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64
+        lib.spectre_mix_abi_version.restype = i32
+        lib.spectre_mix_abi_version.argtypes = []
+        lib.spectre_mix_last_error.restype = ctypes.c_char_p
+        lib.spectre_mix_last_error.argtypes = []
+        lib.spectre_mix_fwd.restype = i32
+        lib.spectre_mix_fwd.argtypes = [vp, i32, i64, i64, vp, vp, i64, vp, i32, i64, i64, i32, i32, i32, i32, i32, vp]
+        lib.spectre_mix_fwd_host.restype = i32
+        lib.spectre_mix_fwd_host.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32]
+        lib.spectre_rfft_fwd.restype = i32
+        lib.spectre_rfft_fwd.argtypes = [vp, i32, i64, i64, vp, i32, i32, i32, i32, vp]
+        lib.spectre_mix_plan.restype = i32
+        lib.spectre_mix_plan.argtypes = [i32, i32, i32, i32, i32, i32, i32, i32, ctypes.POINTER(PlanInfo)]
+        lib.spectre_mix_set_tile_channels.restype = i32
+        lib.spectre_mix_set_tile_channels.argtypes = [i32]
+        lib.spectre_mix_set_prefetch.restype = i32
+        lib.spectre_mix_set_prefetch.argtypes = [i32]
+        _lib = lib
+    return _lib
+
+
+def check(rc: int, what: str):
+    if rc != 0:
+        msg = load().spectre_mix_last_error().decode("utf-8", "replace")
+        raise RuntimeError(f"fft_b200.{what} failed (code {rc}): {msg}")

@@ -1,0 +1,443 @@
+// spectre_mix_api.cu -- C ABI (include/spectre_mix.h), plan selection, twiddle tables, launches.
+//
+// Host-side counterpart of the reference's call sites spectre.py:506, :542-553
+// (forward mix) and :776-777 (prefill rfft).  No torch types, no cuFFT, no CPU
+// fallback: anything this file cannot run returns an error code.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/spectre_mix.h"
+#include "spectre_mix_registry.h"
+
+namespace {
+
+using spx::KernelEntry;
+using spx::MixParams;
+
+thread_local std::string g_err;
+
+int fail(int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+int cuda_fail(cudaError_t e, const char *what) {
+    cudaGetLastError();  // clear the sticky-less error state
+    return fail(SPECTRE_MIX_ERR_CUDA + (int)e, "%s: %s", what, cudaGetErrorString(e));
+}
+
+int g_tile_channels_override = 0;
+int g_prefetch = 1;
+
+// ---------------------------------------------------------------- kernel registry
+const std::vector<KernelEntry> &registry() {
+    static std::vector<KernelEntry> all = [] {
+        std::vector<KernelEntry> v;
+        typedef const KernelEntry *(*TableFn)(int *);
+        TableFn fns[] = {spx::table_small, spx::table_1024, spx::table_2048,
+                         spx::table_4096,  spx::table_8192, spx::table_16384};
+        for (TableFn f : fns) {
+            int n = 0;
+            const KernelEntry *t = f(&n);
+            v.insert(v.end(), t, t + n);
+        }
+        return v;
+    }();
+    return all;
+}
+
+int mode_channels(int mode) { return mode == spx::MODE_QUAD ? 4 : (mode == spx::MODE_PAIR ? 2 : 1); }
+
+// ---------------------------------------------------------------- per-device state
+struct DeviceState {
+    int sm_count = 0;
+    int max_smem_optin = 0;
+    std::map<int, float2 *> twiddles;          // n_fft -> device table
+    std::map<std::pair<const KernelEntry *, int>, int> occupancy;  // (entry, gate_tables*2+has_mem) -> CTAs/SM
+};
+std::mutex g_mu;
+std::map<int, DeviceState> g_dev;
+
+// W_{N/P(s)}^{u q} for every non-final stage, laid out exactly as Plan::TWOFF expects.
+std::vector<float2> build_twiddles(const int radix[4]) {
+    int N = radix[0] * radix[1] * radix[2] * radix[3];
+    int ns = radix[3] > 1 ? 4 : (radix[2] > 1 ? 3 : 2);
+    std::vector<float2> t;
+    int P = 1;
+    for (int s = 0; s < ns - 1; ++s) {
+        const int R = radix[s], L = N / (P * R);
+        for (int q = 1; q < R; ++q)
+            for (int u = 0; u < L; ++u) {
+                // exponent reduced modulo the period before scaling keeps the angle exact in double
+                const long long period = N / P;
+                const long long e = ((long long)u * q) % period;
+                const double ang = -2.0 * M_PI * (double)e / (double)period;
+                t.push_back(make_float2((float)cos(ang), (float)sin(ang)));
+            }
+        P *= R;
+    }
+    return t;
+}
+
+int get_device_state(DeviceState **out, int *dev_out) {
+    int dev = -1;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(SPECTRE_MIX_ERR_NO_DEVICE, "no CUDA device: %s", cudaGetErrorString(e));
+    }
+    DeviceState &st = g_dev[dev];
+    if (st.sm_count == 0) {
+        e = cudaDeviceGetAttribute(&st.sm_count, cudaDevAttrMultiProcessorCount, dev);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaDeviceGetAttribute(SM count)");
+        e = cudaDeviceGetAttribute(&st.max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaDeviceGetAttribute(smem optin)");
+    }
+    *out = &st;
+    if (dev_out) *dev_out = dev;
+    return 0;
+}
+
+int get_twiddles(DeviceState &st, const KernelEntry &k, const float2 **tw) {
+    auto it = st.twiddles.find(k.n_fft);
+    if (it == st.twiddles.end()) {
+        std::vector<float2> h = build_twiddles(k.radix);
+        if ((int)h.size() != k.twn) return fail(SPECTRE_MIX_ERR_BAD_ARG, "internal: twiddle count %zu != %d", h.size(), k.twn);
+        float2 *d = nullptr;
+        cudaError_t e = cudaMalloc(&d, h.size() * sizeof(float2));
+        if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(twiddles)");
+        e = cudaMemcpy(d, h.data(), h.size() * sizeof(float2), cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaMemcpy(twiddles)");
+        it = st.twiddles.emplace(k.n_fft, d).first;
+    }
+    *tw = it->second;
+    return 0;
+}
+
+// ---------------------------------------------------------------- plan selection
+struct Choice {
+    const KernelEntry *k = nullptr;
+    int gate_tables = 1;
+    int tiles_per_row = 0;
+    size_t smem = 0;
+};
+
+bool aligned(const void *p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
+
+// Widest element mode the layout allows: QUAD needs 4 | group_width and 16-byte (fp32) / 8-byte (bf16)
+// aligned rows, PAIR needs 2 | group_width, REAL always works.
+int pick_mode(int dtype, int group_width, const void *v, long long v_sb, long long v_sn, const void *out,
+              long long o_sb, long long o_sn, const void *mem, long long mem_stride) {
+    const size_t es = dtype == SPECTRE_MIX_F32 ? 4 : 2;
+    auto ok = [&](int ch) {
+        if (group_width % ch) return false;
+        const size_t a = es * ch;
+        if (v && !aligned(v, a)) return false;
+        if (out && !aligned(out, a)) return false;
+        if ((v_sb % ch) || (v_sn % ch) || (o_sb % ch) || (o_sn % ch)) return false;
+        if (mem && ch > 1 && (!aligned(mem, 16) || (mem_stride % 2))) return false;
+        return true;
+    };
+    if (ok(4)) return spx::MODE_QUAD;
+    if (ok(2)) return spx::MODE_PAIR;
+    return spx::MODE_REAL;
+}
+
+int choose(const DeviceState &st, int n_fft, int dtype, int mode_max, int C, int group_width, Choice *out) {
+    const std::vector<KernelEntry> &reg = registry();
+    // candidates in registry order (first = default) for the widest mode that has any variant
+    for (int mode = mode_max; mode <= spx::MODE_REAL; ++mode) {
+        const KernelEntry *best = nullptr;
+        Choice bc;
+        for (const KernelEntry &k : reg) {
+            if (k.n_fft != n_fft || k.io != dtype || k.mode != mode) continue;
+            const int ch = mode_channels(mode);
+            const int tw = ch * k.ncol;  // channels per tile
+            if (g_tile_channels_override && tw != g_tile_channels_override) continue;
+            // gate groups a tile can touch (tiles start at multiples of tw)
+            int gt;
+            if (group_width % tw == 0) gt = 1;
+            else if (tw % group_width == 0) gt = tw / group_width;
+            else gt = (tw + group_width - 1) / group_width + 1;
+            const size_t sm = k.smem_bytes(gt);
+            if ((int)sm > st.max_smem_optin) continue;
+            const int ce = C / ch;
+            Choice c;
+            c.k = &k;
+            c.gate_tables = gt;
+            c.tiles_per_row = (ce + k.ncol - 1) / k.ncol;
+            c.smem = sm;
+            if (!best) { best = &k; bc = c; }
+        }
+        if (best) { *out = bc; return 0; }
+        if (g_tile_channels_override) continue;
+    }
+    return fail(SPECTRE_MIX_ERR_UNSUPPORTED,
+                "no kernel variant for n_fft=%d dtype=%d (supported: powers of two in [32, 16384]%s)", n_fft, dtype,
+                g_tile_channels_override ? "; tile override active" : "");
+}
+
+long long algorithmic_bytes(int dtype, bool has_mem, int B, int N, int n_fft, int C, int group_width) {
+    const long long es = dtype == SPECTRE_MIX_F32 ? 4 : 2;
+    const long long n_io = std::min(N, n_fft), fh = n_fft / 2 + 1, ng = C / group_width;
+    return (long long)B * n_io * C * es * 2 + (long long)B * ng * fh * 8 + (has_mem ? fh * C * 8 : 0);
+}
+
+int check_common(int B, int N, int n_fft, int C, int group_width) {
+    if (B < 0 || N < 0 || C < 0) return fail(SPECTRE_MIX_ERR_BAD_ARG, "negative size (B=%d N=%d C=%d)", B, N, C);
+    if (group_width <= 0 || (C % group_width) != 0)
+        return fail(SPECTRE_MIX_ERR_BAD_ARG, "C=%d is not a multiple of group_width=%d", C, group_width);
+    if (n_fft < 32 || n_fft > 16384 || (n_fft & (n_fft - 1)))
+        return fail(SPECTRE_MIX_ERR_UNSUPPORTED, "n_fft=%d unsupported: need a power of two in [32, 16384]", n_fft);
+    return 0;
+}
+
+int occupancy_of(DeviceState &st, const Choice &c, bool has_mem) {
+    auto key = std::make_pair(c.k, c.gate_tables * 2 + (has_mem ? 1 : 0));
+    auto it = st.occupancy.find(key);
+    if (it != st.occupancy.end()) return it->second;
+    int occ = c.k->occupancy(c.gate_tables, has_mem);
+    st.occupancy[key] = occ;
+    return occ;
+}
+
+}  // namespace
+
+extern "C" {
+
+int spectre_mix_abi_version(void) { return 1; }
+
+const char *spectre_mix_last_error(void) { return g_err.c_str(); }
+
+int spectre_mix_set_tile_channels(int tile_channels) {
+    if (tile_channels < 0) return fail(SPECTRE_MIX_ERR_BAD_ARG, "tile_channels < 0");
+    g_tile_channels_override = tile_channels;
+    return 0;
+}
+
+int spectre_mix_set_prefetch(int enable) {
+    g_prefetch = enable ? 1 : 0;
+    return 0;
+}
+
+int spectre_mix_fwd(const void *v, int v_dtype, int64_t v_stride_b, int64_t v_stride_n, const void *gate,
+                    const void *mem, int64_t mem_stride, void *out, int out_dtype, int64_t out_stride_b,
+                    int64_t out_stride_n, int B, int N, int n_fft, int C, int group_width, void *stream) {
+    if (int rc = check_common(B, N, n_fft, C, group_width)) return rc;
+    if (v_dtype != out_dtype || (v_dtype != SPECTRE_MIX_F32 && v_dtype != SPECTRE_MIX_BF16))
+        return fail(SPECTRE_MIX_ERR_UNSUPPORTED, "dtype pair (%d, %d) unsupported: V and out must both be f32 or both bf16",
+                    v_dtype, out_dtype);
+    const int n_io = std::min(N, n_fft);
+    if (B == 0 || C == 0 || n_io == 0) return 0;  // empty input: nothing to write
+    if (!v || !gate || !out) return fail(SPECTRE_MIX_ERR_BAD_ARG, "null pointer (v=%p gate=%p out=%p)", v, gate, out);
+    if (!aligned(gate, 8)) return fail(SPECTRE_MIX_ERR_UNSUPPORTED, "gate must be 8-byte aligned");
+    if (mem && !aligned(mem, 8)) return fail(SPECTRE_MIX_ERR_UNSUPPORTED, "memory must be 8-byte aligned");
+    if (mem && mem_stride < C) return fail(SPECTRE_MIX_ERR_BAD_ARG, "mem_stride=%lld < C=%d", (long long)mem_stride, C);
+
+    std::lock_guard<std::mutex> lock(g_mu);
+    DeviceState *st = nullptr;
+    if (int rc = get_device_state(&st, nullptr)) return rc;
+
+    const int mode = pick_mode(v_dtype, group_width, v, v_stride_b, v_stride_n, out, out_stride_b, out_stride_n, mem,
+                               mem_stride);
+    Choice c;
+    if (int rc = choose(*st, n_fft, v_dtype, mode, C, group_width, &c)) return rc;
+    const float2 *tw = nullptr;
+    if (int rc = get_twiddles(*st, *c.k, &tw)) return rc;
+
+    MixParams p;
+    memset(&p, 0, sizeof(p));
+    p.v = v;
+    p.gate = reinterpret_cast<const float2 *>(gate);
+    p.mem = reinterpret_cast<const float2 *>(mem);
+    p.out = out;
+    p.tw = tw;
+    p.v_sb = v_stride_b;
+    p.v_sn = v_stride_n;
+    p.o_sb = out_stride_b;
+    p.o_sn = out_stride_n;
+    p.mem_stride = mem_stride;
+    p.B = B;
+    p.n_in = n_io;
+    p.n_out = n_io;
+    p.C = C;
+    p.group_width = group_width;
+    p.NG = C / group_width;
+    p.tiles_per_row = c.tiles_per_row;
+    p.num_tiles = B * c.tiles_per_row;
+    p.gate_tables = c.gate_tables;
+    p.inv_n = 1.0f / (float)n_fft;
+    p.prefetch = g_prefetch;
+
+    const int occ = std::max(1, occupancy_of(*st, c, mem != nullptr));
+    const int grid = std::min(p.num_tiles, st->sm_count * occ);
+    cudaError_t e = c.k->launch(p, grid, mem != nullptr, reinterpret_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return cuda_fail(e, "kernel launch");
+    return 0;
+}
+
+int spectre_mix_plan(int v_dtype, int out_dtype, int has_mem, int B, int N, int n_fft, int C, int group_width,
+                     spectre_mix_plan_info *info) {
+    if (!info) return fail(SPECTRE_MIX_ERR_BAD_ARG, "info is null");
+    if (int rc = check_common(B, N, n_fft, C, group_width)) return rc;
+    if (v_dtype != out_dtype) return fail(SPECTRE_MIX_ERR_UNSUPPORTED, "dtype pair unsupported");
+    std::lock_guard<std::mutex> lock(g_mu);
+    DeviceState *st = nullptr;
+    if (int rc = get_device_state(&st, nullptr)) return rc;
+    const int mode = (group_width % 4 == 0) ? spx::MODE_QUAD : ((group_width % 2 == 0) ? spx::MODE_PAIR : spx::MODE_REAL);
+    Choice c;
+    if (int rc = choose(*st, n_fft, v_dtype, mode, C, group_width, &c)) return rc;
+    memset(info, 0, sizeof(*info));
+    info->n_fft = n_fft;
+    for (int i = 0; i < 4; ++i) info->radix[i] = c.k->radix[i];
+    info->tile_channels = mode_channels(c.k->mode) * c.k->ncol;
+    info->threads = c.k->threads;
+    info->ctas_per_sm = std::max(1, occupancy_of(*st, c, has_mem != 0));
+    info->smem_bytes = (int)c.smem;
+    info->grid = std::min(B * c.tiles_per_row, st->sm_count * info->ctas_per_sm);
+    info->launches = 1;
+    info->algorithmic_bytes = algorithmic_bytes(v_dtype, has_mem != 0, B, N, n_fft, C, group_width);
+    return 0;
+}
+
+int spectre_rfft_fwd(const void *v, int v_dtype, int64_t v_stride_b, int64_t v_stride_n, void *spec, int B, int N,
+                     int n_fft, int C, void *stream) {
+    if (int rc = check_common(B, N, n_fft, C, 1)) return rc;
+    if (v_dtype != SPECTRE_MIX_F32 && v_dtype != SPECTRE_MIX_BF16)
+        return fail(SPECTRE_MIX_ERR_UNSUPPORTED, "dtype %d unsupported", v_dtype);
+    if (B == 0 || C == 0) return 0;
+    if (!spec || (!v && N > 0)) return fail(SPECTRE_MIX_ERR_BAD_ARG, "null pointer");
+    if (!aligned(spec, 8)) return fail(SPECTRE_MIX_ERR_UNSUPPORTED, "spec must be 8-byte aligned");
+    std::lock_guard<std::mutex> lock(g_mu);
+    DeviceState *st = nullptr;
+    if (int rc = get_device_state(&st, nullptr)) return rc;
+    Choice c;
+    if (int rc = choose(*st, n_fft, v_dtype, spx::MODE_REAL, C, 1, &c)) return rc;
+    if (!c.k->launch_rfft) return fail(SPECTRE_MIX_ERR_UNSUPPORTED, "internal: no rfft variant");
+    const float2 *tw = nullptr;
+    if (int rc = get_twiddles(*st, *c.k, &tw)) return rc;
+    MixParams p;
+    memset(&p, 0, sizeof(p));
+    p.v = v;
+    p.out = spec;
+    p.tw = tw;
+    p.v_sb = v_stride_b;
+    p.v_sn = v_stride_n;
+    p.o_sb = (long long)(n_fft / 2 + 1) * C;  // complex elements
+    p.o_sn = C;
+    p.B = B;
+    p.n_in = std::min(N, n_fft);
+    p.n_out = 0;
+    p.C = C;
+    p.group_width = 1;
+    p.NG = C;
+    p.tiles_per_row = c.tiles_per_row;
+    p.num_tiles = B * c.tiles_per_row;
+    p.gate_tables = 0;
+    p.inv_n = 1.0f;
+    p.prefetch = 0;
+    const int grid = std::min(p.num_tiles, st->sm_count * std::max(1, c.k->minb));
+    cudaError_t e = c.k->launch_rfft(p, grid, reinterpret_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return cuda_fail(e, "rfft kernel launch");
+    return 0;
+}
+
+// ---------------------------------------------------------------- host-buffer entry point
+namespace {
+struct HostCtx {
+    cudaStream_t s[2] = {nullptr, nullptr};
+    void *dv[2] = {nullptr, nullptr}, *dg[2] = {nullptr, nullptr}, *dout[2] = {nullptr, nullptr};
+    size_t cap_v = 0, cap_g = 0;
+    void *dmem = nullptr;
+    size_t cap_mem = 0;
+};
+std::mutex g_host_mu;
+std::map<int, HostCtx> g_host;
+}  // namespace
+
+int spectre_mix_fwd_host(const float *v, const float *gate, const float *mem, float *out, int B, int N, int n_fft,
+                         int C, int group_width) {
+    if (int rc = check_common(B, N, n_fft, C, group_width)) return rc;
+    const int n_io = std::min(N, n_fft);
+    if (B == 0 || C == 0 || n_io == 0) return 0;
+    if (!v || !gate || !out) return fail(SPECTRE_MIX_ERR_BAD_ARG, "null pointer");
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(SPECTRE_MIX_ERR_NO_DEVICE, "no CUDA device: %s", cudaGetErrorString(e));
+    }
+    std::lock_guard<std::mutex> lock(g_host_mu);
+    HostCtx &h = g_host[dev];
+    const size_t fh = n_fft / 2 + 1, ng = C / group_width;
+    const size_t row_v = (size_t)N * C * 4, row_o = (size_t)n_io * C * 4, row_g = ng * fh * 8;
+    // batch rows per chunk: ~48 MB of V per chunk keeps both copy engines and the SMs busy
+    const int rows = (int)std::max<size_t>(1, std::min<size_t>((size_t)B, (48u << 20) / std::max<size_t>(row_v, 1)));
+    const size_t need_v = std::max(row_v, row_o) * rows, need_g = row_g * rows;
+    for (int i = 0; i < 2; ++i) {
+        if (!h.s[i] && (e = cudaStreamCreateWithFlags(&h.s[i], cudaStreamNonBlocking)) != cudaSuccess)
+            return cuda_fail(e, "cudaStreamCreate");
+    }
+    if (need_v > h.cap_v) {
+        for (int i = 0; i < 2; ++i) {
+            cudaFree(h.dv[i]);
+            cudaFree(h.dout[i]);
+            if ((e = cudaMalloc(&h.dv[i], need_v)) != cudaSuccess) return cuda_fail(e, "cudaMalloc(V chunk)");
+            if ((e = cudaMalloc(&h.dout[i], need_v)) != cudaSuccess) return cuda_fail(e, "cudaMalloc(out chunk)");
+        }
+        h.cap_v = need_v;
+    }
+    if (need_g > h.cap_g) {
+        for (int i = 0; i < 2; ++i) {
+            cudaFree(h.dg[i]);
+            if ((e = cudaMalloc(&h.dg[i], need_g)) != cudaSuccess) return cuda_fail(e, "cudaMalloc(gate chunk)");
+        }
+        h.cap_g = need_g;
+    }
+    if (mem) {
+        const size_t need_m = fh * (size_t)C * 8;
+        if (need_m > h.cap_mem) {
+            cudaFree(h.dmem);
+            if ((e = cudaMalloc(&h.dmem, need_m)) != cudaSuccess) return cuda_fail(e, "cudaMalloc(memory)");
+            h.cap_mem = need_m;
+        }
+        if ((e = cudaMemcpyAsync(h.dmem, mem, need_m, cudaMemcpyHostToDevice, h.s[0])) != cudaSuccess)
+            return cuda_fail(e, "cudaMemcpyAsync(memory)");
+        if ((e = cudaStreamSynchronize(h.s[0])) != cudaSuccess) return cuda_fail(e, "sync(memory)");
+    }
+    int chunk = 0;
+    for (int b0 = 0; b0 < B; b0 += rows, ++chunk) {
+        const int nb = std::min(rows, B - b0);
+        const int i = chunk & 1;
+        cudaStream_t s = h.s[i];
+        if ((e = cudaMemcpyAsync(h.dv[i], v + (size_t)b0 * N * C, row_v * nb, cudaMemcpyHostToDevice, s)) != cudaSuccess)
+            return cuda_fail(e, "H2D V");
+        if ((e = cudaMemcpyAsync(h.dg[i], reinterpret_cast<const char *>(gate) + (size_t)b0 * row_g, row_g * nb,
+                                 cudaMemcpyHostToDevice, s)) != cudaSuccess)
+            return cuda_fail(e, "H2D gate");
+        int rc = spectre_mix_fwd(h.dv[i], SPECTRE_MIX_F32, (int64_t)N * C, C, h.dg[i], mem ? h.dmem : nullptr, C, h.dout[i],
+                                 SPECTRE_MIX_F32, (int64_t)n_io * C, C, nb, N, n_fft, C, group_width, s);
+        if (rc) return rc;
+        if ((e = cudaMemcpyAsync(out + (size_t)b0 * n_io * C, h.dout[i], row_o * nb, cudaMemcpyDeviceToHost, s)) !=
+            cudaSuccess)
+            return cuda_fail(e, "D2H out");
+    }
+    for (int i = 0; i < 2; ++i)
+        if ((e = cudaStreamSynchronize(h.s[i])) != cudaSuccess) return cuda_fail(e, "stream sync");
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,572 @@
+// spectre_mix_kernel.cuh -- fused rFFT -> gate (+memory) -> irFFT for sm_100a.
+//
+// Replaces /root/reference/spectre.py:506 (torch.fft.rfft), :542-545 (gate
+// broadcast + complex multiply), :548-549 (memory add), :551 (torch.fft.irfft),
+// :553 ([:N]) and the per-head loop of :703-718 with ONE persistent kernel.
+//
+// How the path is mapped onto B200 (details in DESIGN.md):
+//   * The transform axis is the strided one (V is [B][N][C], channels contiguous),
+//     so a CTA owns ALL n_fft rows of a narrow channel tile of one batch row and
+//     keeps them in shared memory for the whole rfft->gate->irfft round trip:
+//     HBM sees each input element once and each output element once.
+//   * Four adjacent channels (c..c+3, same gate group) form one tile "element":
+//     two complex signals z0 = v[c] + i v[c+2], z1 = v[c+1] + i v[c+3].  Because the
+//     gate acts as a real convolution kernel (irfft drops imag(DC), imag(Nyquist)),
+//     ifft(Gfull * fft(z)) returns the two real results in Re and Im -- half the
+//     FFT work and no real-FFT post-processing.  z0 and z1 ride in the two lanes
+//     of Blackwell's packed fp32x2 pipe (FADD2 / FMUL2 / FFMA2): every butterfly
+//     instruction does two columns, twiddles are broadcast scalar operands.
+//   * FFT = in-place mixed radix (r,16,16[,16]) decimation in frequency going
+//     forward, the exact mirror (decimation in time) coming back, so no digit
+//     reversal pass exists: the gate is applied in digit-reversed order, and the
+//     last forward butterfly, the gate multiply and the first inverse butterfly
+//     are one register-resident pass.
+//   * Inverse transform = forward butterflies on (im, re)-swapped data, so one
+//     twiddle table serves both directions.
+//   * Shared-memory element index e is stored at e + (e >> 4): every pass (strides
+//     n_fft/r, 16, 1) is bank-conflict free with 128-bit accesses.
+//   * Loads/stores are 128-bit, sector-complete per warp instruction; the next
+//     tile of a CTA is prefetched into the 126 MB L2 while the current one is
+//     being transformed (L2 is the landing buffer -- a 4096x8 fp32 tile fills
+//     shared memory on its own).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+namespace spx {
+
+enum Mode : int { MODE_QUAD = 0, MODE_PAIR = 1, MODE_REAL = 2 };
+
+struct MixParams {
+    const void *v;
+    const float2 *gate;   // [B][NG][F_half]
+    const float2 *mem;    // [F_half][C] (row stride mem_stride) or nullptr
+    void *out;            // mix: [B][n_out][C] real; rfft-only: complex64 [B][F_half][C]
+    const float2 *tw;     // per-plan twiddle table (device)
+    long long v_sb, v_sn, o_sb, o_sn, mem_stride;
+    int B, n_in, n_out, C, group_width, NG;
+    int tiles_per_row, num_tiles;
+    int gate_tables;      // gate groups a tile may touch (smem sized for this many)
+    float inv_n;
+    int prefetch;         // 1: prefetch the CTA's next tile into L2 while this one is transformed
+};
+
+// ------------------------------------------------------------------ packed / scalar lanes
+__device__ __forceinline__ float2 vadd(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 vsub(float2 a, float2 b) { return __fadd2_rn(a, make_float2(-b.x, -b.y)); }
+__device__ __forceinline__ float2 vmul(float2 a, float s) { return __fmul2_rn(a, make_float2(s, s)); }
+__device__ __forceinline__ float2 vfma(float2 a, float s, float2 c) { return __ffma2_rn(a, make_float2(s, s), c); }
+__device__ __forceinline__ float2 vfnma(float2 a, float s, float2 c) { return __ffma2_rn(a, make_float2(-s, -s), c); }
+__device__ __forceinline__ float2 vzero(float2) { return make_float2(0.f, 0.f); }
+__device__ __forceinline__ float2 vneg(float2 a) { return make_float2(-a.x, -a.y); }
+
+__device__ __forceinline__ float vadd(float a, float b) { return a + b; }
+__device__ __forceinline__ float vsub(float a, float b) { return a - b; }
+__device__ __forceinline__ float vmul(float a, float s) { return a * s; }
+__device__ __forceinline__ float vfma(float a, float s, float c) { return fmaf(a, s, c); }
+__device__ __forceinline__ float vfnma(float a, float s, float c) { return fmaf(-a, s, c); }
+__device__ __forceinline__ float vzero(float) { return 0.f; }
+__device__ __forceinline__ float vneg(float a) { return -a; }
+
+template <class V>
+struct Cx {
+    V re, im;
+};
+
+template <class V>
+__device__ __forceinline__ Cx<V> cadd(const Cx<V> &a, const Cx<V> &b) { return {vadd(a.re, b.re), vadd(a.im, b.im)}; }
+template <class V>
+__device__ __forceinline__ Cx<V> csub(const Cx<V> &a, const Cx<V> &b) { return {vsub(a.re, b.re), vsub(a.im, b.im)}; }
+// a * (wr + i wi), wr/wi scalars shared by both packed lanes
+template <class V>
+__device__ __forceinline__ Cx<V> cmul(const Cx<V> &a, float wr, float wi) {
+    Cx<V> r;
+    r.re = vfnma(a.im, wi, vmul(a.re, wr));
+    r.im = vfma(a.im, wr, vmul(a.re, wi));
+    return r;
+}
+// a * conj(wr + i wi)
+template <class V>
+__device__ __forceinline__ Cx<V> cmulc(const Cx<V> &a, float wr, float wi) {
+    Cx<V> r;
+    r.re = vfma(a.im, wi, vmul(a.re, wr));
+    r.im = vfnma(a.re, wi, vmul(a.im, wr));
+    return r;
+}
+template <class V>
+__device__ __forceinline__ Cx<V> cswap(const Cx<V> &a) { return {a.im, a.re}; }
+
+// ------------------------------------------------------------------ small DFTs (forward sign, natural order out)
+template <class V>
+__device__ __forceinline__ void dft2(Cx<V> &a, Cx<V> &b) {
+    Cx<V> t = a;
+    a = cadd(t, b);
+    b = csub(t, b);
+}
+template <class V>
+__device__ __forceinline__ void dft4(Cx<V> &x0, Cx<V> &x1, Cx<V> &x2, Cx<V> &x3) {
+    Cx<V> t0 = cadd(x0, x2), t1 = csub(x0, x2), t2 = cadd(x1, x3), t3 = csub(x1, x3);
+    x0 = cadd(t0, t2);
+    x2 = csub(t0, t2);
+    x1.re = vadd(t1.re, t3.im);  // t1 - i t3
+    x1.im = vsub(t1.im, t3.re);
+    x3.re = vsub(t1.re, t3.im);  // t1 + i t3
+    x3.im = vadd(t1.im, t3.re);
+}
+
+template <int R, class V>
+struct Dft;
+template <class V>
+struct Dft<2, V> {
+    static __device__ __forceinline__ void run(Cx<V> (&x)[2]) { dft2(x[0], x[1]); }
+};
+template <class V>
+struct Dft<4, V> {
+    static __device__ __forceinline__ void run(Cx<V> (&x)[4]) { dft4(x[0], x[1], x[2], x[3]); }
+};
+template <class V>
+struct Dft<8, V> {
+    static __device__ __forceinline__ void run(Cx<V> (&x)[8]) {
+        constexpr float h = 0.70710678118654752440f;
+        dft4(x[0], x[2], x[4], x[6]);
+        dft4(x[1], x[3], x[5], x[7]);
+        x[3] = cmul(x[3], h, -h);                       // W8^1
+        { Cx<V> t = x[5]; x[5].re = t.im; x[5].im = vneg(t.re); }  // W8^2 = -i
+        x[7] = cmul(x[7], -h, -h);                      // W8^3
+        Cx<V> y[8];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            dft2(x[2 * q], x[2 * q + 1]);
+            y[q] = x[2 * q];
+            y[q + 4] = x[2 * q + 1];
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) x[q] = y[q];
+    }
+};
+template <class V>
+struct Dft<16, V> {
+    static __device__ __forceinline__ void run(Cx<V> (&x)[16]) {
+        // n = n0 + 4 n1, q = q1 + 4 q0:  W16^{nq} = W4^{n1 q1} W16^{n0 q1} W4^{n0 q0}
+        constexpr float c1 = 0.92387953251128675613f, s1 = 0.38268343236508977173f;
+        constexpr float h = 0.70710678118654752440f;
+#pragma unroll
+        for (int n0 = 0; n0 < 4; ++n0) dft4(x[n0], x[n0 + 4], x[n0 + 8], x[n0 + 12]);
+        // x[n0 + 4 q1] *= W16^{n0 q1}
+        x[1 + 4] = cmul(x[1 + 4], c1, -s1);     // W^1
+        x[1 + 8] = cmul(x[1 + 8], h, -h);       // W^2
+        x[1 + 12] = cmul(x[1 + 12], s1, -c1);   // W^3
+        x[2 + 4] = cmul(x[2 + 4], h, -h);       // W^2
+        { Cx<V> t = x[2 + 8]; x[2 + 8].re = t.im; x[2 + 8].im = vneg(t.re); }  // W^4 = -i
+        x[2 + 12] = cmul(x[2 + 12], -h, -h);    // W^6
+        x[3 + 4] = cmul(x[3 + 4], s1, -c1);     // W^3
+        x[3 + 8] = cmul(x[3 + 8], -h, -h);      // W^6
+        x[3 + 12] = cmul(x[3 + 12], -c1, s1);   // W^9
+        Cx<V> y[16];
+#pragma unroll
+        for (int q1 = 0; q1 < 4; ++q1) {
+            dft4(x[4 * q1], x[4 * q1 + 1], x[4 * q1 + 2], x[4 * q1 + 3]);
+#pragma unroll
+            for (int q0 = 0; q0 < 4; ++q0) y[q1 + 4 * q0] = x[4 * q1 + q0];
+        }
+#pragma unroll
+        for (int q = 0; q < 16; ++q) x[q] = y[q];
+    }
+};
+
+// ------------------------------------------------------------------ plan (compile time)
+template <int R0, int R1, int R2, int R3>
+struct Plan {
+    static constexpr int N = R0 * R1 * R2 * R3;
+    static constexpr int NS = (R3 > 1) ? 4 : ((R2 > 1) ? 3 : ((R1 > 1) ? 2 : 1));
+    static_assert(NS >= 2, "at least two stages");
+    __host__ __device__ static constexpr int R(int s) { return s == 0 ? R0 : (s == 1 ? R1 : (s == 2 ? R2 : R3)); }
+    __host__ __device__ static constexpr int P(int s) { return s == 0 ? 1 : (s == 1 ? R0 : (s == 2 ? R0 * R1 : R0 * R1 * R2)); }
+    __host__ __device__ static constexpr int L(int s) { return N / (P(s) * R(s)); }
+    // twiddles of stage s (s < NS-1): W_{N/P}^{u q}, stored at TWOFF(s) + (q-1) L + u
+    __host__ __device__ static constexpr int TWOFF(int s) { return s == 0 ? 0 : TWOFF(s - 1) + (R(s - 1) - 1) * L(s - 1); }
+    static constexpr int TWN = TWOFF(NS - 1);
+    static constexpr int NPAD = N + (N >> 4);
+    static constexpr int GPAD = (N / 2) + ((N / 2) >> 4) + 1;  // padded gate table length (float2)
+};
+
+__host__ __device__ constexpr int cmax(int a, int b) { return a > b ? a : b; }
+
+// ------------------------------------------------------------------ element traits per mode
+template <int MODE>
+struct Elem;
+template <>
+struct Elem<MODE_QUAD> {
+    using V = float2;
+    using S = float4;
+    static constexpr int CH = 4;     // channels per element
+    static constexpr int WAVE = 8;   // lanes per shared-memory wavefront for S
+    static __device__ __forceinline__ Cx<V> unpack(const S &f) { return {make_float2(f.x, f.y), make_float2(f.z, f.w)}; }
+    static __device__ __forceinline__ S pack(const Cx<V> &c) { return make_float4(c.re.x, c.re.y, c.im.x, c.im.y); }
+};
+template <>
+struct Elem<MODE_PAIR> {
+    using V = float;
+    using S = float2;
+    static constexpr int CH = 2;
+    static constexpr int WAVE = 16;
+    static __device__ __forceinline__ Cx<V> unpack(const S &f) { return {f.x, f.y}; }
+    static __device__ __forceinline__ S pack(const Cx<V> &c) { return make_float2(c.re, c.im); }
+};
+template <>
+struct Elem<MODE_REAL> {
+    using V = float;
+    using S = float2;
+    static constexpr int CH = 1;
+    static constexpr int WAVE = 16;
+    static __device__ __forceinline__ Cx<V> unpack(const S &f) { return {f.x, f.y}; }
+    static __device__ __forceinline__ S pack(const Cx<V> &c) { return make_float2(c.re, c.im); }
+};
+
+// global loads/stores of one element (CH channels of one row) --------------------------------
+template <int MODE, class IO>
+struct GIO;
+
+template <>
+struct GIO<MODE_QUAD, float> {
+    static __device__ __forceinline__ Cx<float2> load(const float *p) {
+        float4 f = __ldcs(reinterpret_cast<const float4 *>(p));
+        return {make_float2(f.x, f.y), make_float2(f.z, f.w)};
+    }
+    static __device__ __forceinline__ void store(float *p, const Cx<float2> &c) {
+        __stcs(reinterpret_cast<float4 *>(p), make_float4(c.re.x, c.re.y, c.im.x, c.im.y));
+    }
+};
+template <>
+struct GIO<MODE_QUAD, __nv_bfloat16> {
+    static __device__ __forceinline__ Cx<float2> load(const __nv_bfloat16 *p) {
+        uint2 r = __ldcs(reinterpret_cast<const uint2 *>(p));
+        __nv_bfloat162 a = *reinterpret_cast<__nv_bfloat162 *>(&r.x), b = *reinterpret_cast<__nv_bfloat162 *>(&r.y);
+        return {__bfloat1622float2(a), __bfloat1622float2(b)};
+    }
+    static __device__ __forceinline__ void store(__nv_bfloat16 *p, const Cx<float2> &c) {
+        __nv_bfloat162 a = __float22bfloat162_rn(c.re), b = __float22bfloat162_rn(c.im);
+        uint2 r;
+        r.x = *reinterpret_cast<unsigned *>(&a);
+        r.y = *reinterpret_cast<unsigned *>(&b);
+        __stcs(reinterpret_cast<uint2 *>(p), r);
+    }
+};
+template <>
+struct GIO<MODE_PAIR, float> {
+    static __device__ __forceinline__ Cx<float> load(const float *p) {
+        float2 f = __ldcs(reinterpret_cast<const float2 *>(p));
+        return {f.x, f.y};
+    }
+    static __device__ __forceinline__ void store(float *p, const Cx<float> &c) {
+        __stcs(reinterpret_cast<float2 *>(p), make_float2(c.re, c.im));
+    }
+};
+template <>
+struct GIO<MODE_PAIR, __nv_bfloat16> {
+    static __device__ __forceinline__ Cx<float> load(const __nv_bfloat16 *p) {
+        unsigned r = __ldcs(reinterpret_cast<const unsigned *>(p));
+        float2 f = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162 *>(&r));
+        return {f.x, f.y};
+    }
+    static __device__ __forceinline__ void store(__nv_bfloat16 *p, const Cx<float> &c) {
+        __nv_bfloat162 a = __float22bfloat162_rn(make_float2(c.re, c.im));
+        __stcs(reinterpret_cast<unsigned *>(p), *reinterpret_cast<unsigned *>(&a));
+    }
+};
+template <>
+struct GIO<MODE_REAL, float> {
+    static __device__ __forceinline__ Cx<float> load(const float *p) { return {__ldcs(p), 0.f}; }
+    static __device__ __forceinline__ void store(float *p, const Cx<float> &c) { __stcs(p, c.re); }
+};
+template <>
+struct GIO<MODE_REAL, __nv_bfloat16> {
+    static __device__ __forceinline__ Cx<float> load(const __nv_bfloat16 *p) { return {__bfloat162float(*p), 0.f}; }
+    static __device__ __forceinline__ void store(__nv_bfloat16 *p, const Cx<float> &c) { *p = __float2bfloat16_rn(c.re); }
+};
+
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+// ------------------------------------------------------------------ shared memory layout
+template <class PL, int MODE, int NCOL>
+struct Smem {
+    using E = Elem<MODE>;
+    static constexpr int SKEW = cmax(1, E::WAVE / NCOL);
+    static constexpr int CS = PL::NPAD + SKEW;                 // column stride in elements
+    static constexpr size_t data_bytes = sizeof(typename E::S) * (size_t)CS * NCOL;
+    static constexpr size_t tw_bytes = ((sizeof(float2) * (size_t)PL::TWN + 15) / 16) * 16;
+    static constexpr size_t gate_bytes_one = ((sizeof(float2) * (size_t)PL::GPAD + 15) / 16) * 16;
+    static constexpr size_t bytes(int gate_tables) { return data_bytes + tw_bytes + gate_bytes_one * (size_t)gate_tables; }
+};
+
+// stage-s butterfly id -> frequency digits: k_low = sum_{i < NS-1} q_i P(i), given Q of the last stage
+template <class PL>
+__device__ __forceinline__ int klow_of(int Q) {
+    // Q = ((q_0 R_1 + q_1) R_2 + q_2) ...  over stages 0 .. NS-2
+    int k = 0;
+#pragma unroll
+    for (int s = PL::NS - 2; s >= 0; --s) {
+        int q = Q % PL::R(s);
+        Q /= PL::R(s);
+        k += q * PL::P(s);
+    }
+    return k;
+}
+
+// ------------------------------------------------------------------ in-place inner passes (stages 1 .. NS-2)
+// Butterfly bf = Q * L + u of a column works on elements Q*(R*L) + m*L + u, m < R, and leaves output
+// digit q in the slot of input m = q, so no pass ever moves data between slots.
+template <class PL, int MODE, int NCOL, int NT, int S_>
+__device__ __forceinline__ void fwd_inner_pass(typename Elem<MODE>::S *buf, const float2 *tw, int tid) {
+    using E = Elem<MODE>;
+    using V = typename E::V;
+    constexpr int R = PL::R(S_), L = PL::L(S_), NBF = PL::N / R, ITEMS = NCOL * NBF;
+    constexpr int CS = Smem<PL, MODE, NCOL>::CS;
+    static_assert(L % 16 == 0 || L == 1, "offset padding assumes 16 | L");
+    for (int w = tid; w < ITEMS; w += NT) {
+        const int col = w / NBF, bf = w - col * NBF;
+        const int Q = bf / L, u = bf - Q * L;
+        const int e0 = Q * (R * L) + u;
+        typename E::S *cb = buf + col * CS + e0 + (e0 >> 4);
+        Cx<V> x[R];
+#pragma unroll
+        for (int m = 0; m < R; ++m) x[m] = E::unpack(cb[m * L + ((m * L) >> 4)]);
+        Dft<R, V>::run(x);
+        const float2 *tws = tw + PL::TWOFF(S_) + u;
+#pragma unroll
+        for (int q = 1; q < R; ++q) {
+            const float2 wq = tws[(q - 1) * L];
+            x[q] = cmul(x[q], wq.x, wq.y);
+        }
+#pragma unroll
+        for (int q = 0; q < R; ++q) cb[q * L + ((q * L) >> 4)] = E::pack(x[q]);
+    }
+}
+
+// inverse of the above: conj-twiddle then inverse butterfly, done as forward arithmetic on (im, re)
+template <class PL, int MODE, int NCOL, int NT, int S_>
+__device__ __forceinline__ void inv_inner_pass(typename Elem<MODE>::S *buf, const float2 *tw, int tid) {
+    using E = Elem<MODE>;
+    using V = typename E::V;
+    constexpr int R = PL::R(S_), L = PL::L(S_), NBF = PL::N / R, ITEMS = NCOL * NBF;
+    constexpr int CS = Smem<PL, MODE, NCOL>::CS;
+    for (int w = tid; w < ITEMS; w += NT) {
+        const int col = w / NBF, bf = w - col * NBF;
+        const int Q = bf / L, u = bf - Q * L;
+        const int e0 = Q * (R * L) + u;
+        typename E::S *cb = buf + col * CS + e0 + (e0 >> 4);
+        const float2 *tws = tw + PL::TWOFF(S_) + u;
+        Cx<V> x[R];
+#pragma unroll
+        for (int q = 0; q < R; ++q) {
+            x[q] = cswap(E::unpack(cb[q * L + ((q * L) >> 4)]));
+            if (q > 0) {
+                const float2 wq = tws[(q - 1) * L];
+                x[q] = cmul(x[q], wq.x, wq.y);
+            }
+        }
+        Dft<R, V>::run(x);
+#pragma unroll
+        for (int m = 0; m < R; ++m) cb[m * L + ((m * L) >> 4)] = E::pack(cswap(x[m]));
+    }
+}
+
+// spectral-memory add (spectre.py:548-549) on packed elements; sgn = +inv_n (bin k), -inv_n (mirror bin,
+// conjugated) or 0 (imag of DC / Nyquist ignored, as irfft does)
+__device__ __forceinline__ void mem_add(Cx<float2> &x, const float2 *mp, float inv_n, float sgn, int /*mode*/) {
+    // channels c..c+3: z0 = ch0 + i ch2, z1 = ch1 + i ch3;  M_ch = a_ch + i b_ch
+    const float4 m01 = __ldg(reinterpret_cast<const float4 *>(mp));
+    const float4 m23 = __ldg(reinterpret_cast<const float4 *>(mp) + 1);
+    x.re.x += m01.x * inv_n - m23.y * sgn;
+    x.re.y += m01.z * inv_n - m23.w * sgn;
+    x.im.x += m23.x * inv_n + m01.y * sgn;
+    x.im.y += m23.z * inv_n + m01.w * sgn;
+}
+__device__ __forceinline__ void mem_add(Cx<float> &x, const float2 *mp, float inv_n, float sgn, int mode) {
+    if (mode == MODE_PAIR) {  // z = ch0 + i ch1
+        const float4 m01 = __ldg(reinterpret_cast<const float4 *>(mp));
+        x.re += m01.x * inv_n - m01.w * sgn;
+        x.im += m01.z * inv_n + m01.y * sgn;
+    } else {                  // z = ch0
+        const float2 m0 = __ldg(mp);
+        x.re += m0.x * inv_n;
+        x.im += m0.y * sgn;
+    }
+}
+
+// ------------------------------------------------------------------ the kernel
+// KIND 0: full mix (rfft -> gate (+mem) -> irfft);  KIND 1: rfft only (half spectrum out, MODE_PAIR/REAL... see api)
+template <class PL, int MODE, int NCOL, int NT, int MINB, class TIN, class TOUT, bool HAS_MEM, bool RFFT_ONLY = false>
+__global__ void __launch_bounds__(NT, MINB) spectre_mix_kernel(const MixParams p) {
+    using E = Elem<MODE>;
+    using V = typename E::V;
+    using S = typename E::S;
+    using SM = Smem<PL, MODE, NCOL>;
+    constexpr int N = PL::N, NS = PL::NS, CH = E::CH, CS = SM::CS;
+    constexpr int RL = PL::R(NS - 1);       // radix of the last stage (fused middle pass)
+    constexpr int PLAST = PL::P(NS - 1);    // = N / RL
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    S *buf = reinterpret_cast<S *>(smem_raw);
+    float2 *tw = reinterpret_cast<float2 *>(smem_raw + SM::data_bytes);
+    float2 *gate_s = reinterpret_cast<float2 *>(smem_raw + SM::data_bytes + SM::tw_bytes);
+    constexpr int GS = (int)(SM::gate_bytes_one / sizeof(float2));
+
+    const int tid = threadIdx.x;
+    for (int i = tid; i < PL::TWN; i += NT) tw[i] = p.tw[i];
+    // first __syncthreads of the tile loop publishes the table
+
+    const TIN *vbase = reinterpret_cast<const TIN *>(p.v);
+    TOUT *obase = reinterpret_cast<TOUT *>(p.out);
+    const int CE = p.C / CH;  // elements per row
+
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        const int b = tile / p.tiles_per_row;
+        const int ce0 = (tile - b * p.tiles_per_row) * NCOL;  // first element column of the tile
+        const int c0 = ce0 * CH;
+        const int g0 = c0 / p.group_width;
+
+        // ---- stage the gate tables of this tile (scaled by 1/n_fft, imag(DC)=imag(Nyquist)=0)
+        for (int t = 0; t < p.gate_tables; ++t) {
+            const int g = g0 + t;
+            if (g < p.NG) {
+                const float2 *gp = p.gate + ((long long)b * p.NG + g) * (N / 2 + 1);
+                for (int k = tid; k <= N / 2; k += NT) {
+                    float2 gv = __ldg(gp + k);
+                    gv.x *= p.inv_n;
+                    gv.y = (k == 0 || k == N / 2) ? 0.f : gv.y * p.inv_n;
+                    gate_s[t * GS + k + (k >> 4)] = gv;
+                }
+            }
+        }
+
+        // ---- forward stage 0: global -> butterfly -> twiddle -> smem
+        {
+            constexpr int R = PL::R(0), L = PL::L(0);
+            constexpr int ITEMS = NCOL * L;
+            const TIN *vb = vbase + (long long)b * p.v_sb + c0;
+            const int next_tile = tile + gridDim.x;
+            const TIN *vnext = nullptr;
+            if (p.prefetch && next_tile < p.num_tiles) {
+                const int nb = next_tile / p.tiles_per_row;
+                vnext = vbase + (long long)nb * p.v_sb + (long long)(next_tile - nb * p.tiles_per_row) * NCOL * CH;
+            }
+            for (int w = tid; w < ITEMS; w += NT) {
+                const int col = w % NCOL, u = w / NCOL;
+                const bool colok = (ce0 + col) < CE;
+                Cx<V> x[R];
+#pragma unroll
+                for (int m = 0; m < R; ++m) {
+                    const int row = u + m * L;
+                    if (colok && row < p.n_in) x[m] = GIO<MODE, TIN>::load(vb + (long long)row * p.v_sn + col * CH);
+                    else x[m] = {vzero(V()), vzero(V())};
+                }
+                if (vnext != nullptr && colok) {
+#pragma unroll
+                    for (int m = 0; m < R; ++m) {
+                        const int row = u + m * L;
+                        if (row < p.n_in) prefetch_l2(vnext + (long long)row * p.v_sn + col * CH);
+                    }
+                }
+                Dft<R, V>::run(x);
+                const float2 *tws = tw + PL::TWOFF(0) + u;
+#pragma unroll
+                for (int q = 1; q < R; ++q) {
+                    const float2 wq = tws[(q - 1) * L];
+                    x[q] = cmul(x[q], wq.x, wq.y);
+                }
+                S *cb = buf + col * CS + u + (u >> 4);
+#pragma unroll
+                for (int q = 0; q < R; ++q) cb[q * L + ((q * L) >> 4)] = E::pack(x[q]);
+            }
+        }
+        __syncthreads();
+
+        // ---- forward stages 1 .. NS-2: smem -> butterfly -> twiddle -> smem (in place)
+        if constexpr (NS > 2) { fwd_inner_pass<PL, MODE, NCOL, NT, 1>(buf, tw, tid); __syncthreads(); }
+        if constexpr (NS > 3) { fwd_inner_pass<PL, MODE, NCOL, NT, 2>(buf, tw, tid); __syncthreads(); }
+
+        // ---- middle pass: last forward butterfly -> gate (+memory) -> first inverse butterfly
+        {
+            constexpr int NBF = N / RL, ITEMS = NCOL * NBF;
+            for (int w = tid; w < ITEMS; w += NT) {
+                const int col = w / NBF, Q = w - col * NBF;
+                if ((ce0 + col) >= CE) continue;   // column past the last channel: nothing to transform
+                const int e0 = Q * RL;
+                S *cb = buf + col * CS + e0 + (e0 >> 4);
+                Cx<V> x[RL];
+#pragma unroll
+                for (int m = 0; m < RL; ++m) x[m] = E::unpack(cb[m]);
+                Dft<RL, V>::run(x);
+                const int klow = klow_of<PL>(Q);
+                const int cabs = (ce0 + col) * CH;                 // first channel of this element
+                if constexpr (RFFT_ONLY) {
+                    // half spectrum out (spectre.py:506 / :777): bins k <= n_fft/2 of this channel
+                    if ((ce0 + col) < CE) {
+                        float2 *sp = reinterpret_cast<float2 *>(p.out) + (long long)b * p.o_sb + cabs;
+#pragma unroll
+                        for (int q = 0; q < RL; ++q) {
+                            const int k = klow + PLAST * q;
+                            if (k <= N / 2) sp[(long long)k * p.o_sn] = E::pack(x[q]);
+                        }
+                    }
+                    continue;
+                }
+                const float2 *gs = gate_s + (cabs / p.group_width - g0) * GS;
+#pragma unroll
+                for (int q = 0; q < RL; ++q) {
+                    const bool lower = q < RL / 2 || RL == 1;
+                    const int k = lower ? (klow + PLAST * q) : (N - klow - PLAST * q);  // table index (<= N/2)
+                    const float2 g = gs[k + (k >> 4)];
+                    x[q] = lower ? cmul(x[q], g.x, g.y) : cmulc(x[q], g.x, g.y);
+                    if (HAS_MEM) {
+                        const float sgn = ((q == 0 || q == RL / 2) && klow == 0) ? 0.f : (lower ? p.inv_n : -p.inv_n);
+                        mem_add(x[q], p.mem + (long long)k * p.mem_stride + cabs, p.inv_n, sgn, MODE);
+                    }
+                    x[q] = cswap(x[q]);
+                }
+                Dft<RL, V>::run(x);
+#pragma unroll
+                for (int m = 0; m < RL; ++m) cb[m] = E::pack(cswap(x[m]));
+            }
+        }
+        __syncthreads();
+        if constexpr (RFFT_ONLY) continue;
+
+        // ---- inverse stages NS-2 .. 1: smem -> twiddle -> butterfly -> smem (in place)
+        if constexpr (NS > 3) { inv_inner_pass<PL, MODE, NCOL, NT, 2>(buf, tw, tid); __syncthreads(); }
+        if constexpr (NS > 2) { inv_inner_pass<PL, MODE, NCOL, NT, 1>(buf, tw, tid); __syncthreads(); }
+
+        // ---- inverse stage 0: smem -> twiddle -> butterfly -> global
+        {
+            constexpr int R = PL::R(0), L = PL::L(0);
+            constexpr int ITEMS = NCOL * L;
+            TOUT *ob = obase + (long long)b * p.o_sb + c0;
+            for (int w = tid; w < ITEMS; w += NT) {
+                const int col = w % NCOL, u = w / NCOL;
+                const bool colok = (ce0 + col) < CE;
+                const S *cb = buf + col * CS + u + (u >> 4);
+                const float2 *tws = tw + PL::TWOFF(0) + u;
+                Cx<V> x[R];
+#pragma unroll
+                for (int q = 0; q < R; ++q) {
+                    x[q] = cswap(E::unpack(cb[q * L + ((q * L) >> 4)]));
+                    if (q > 0) {
+                        const float2 wq = tws[(q - 1) * L];
+                        x[q] = cmul(x[q], wq.x, wq.y);
+                    }
+                }
+                Dft<R, V>::run(x);
+#pragma unroll
+                for (int m = 0; m < R; ++m) {
+                    const int row = u + m * L;
+                    if (colok && row < p.n_out) GIO<MODE, TOUT>::store(ob + (long long)row * p.o_sn + col * CH, cswap(x[m]));
+                }
+            }
+        }
+        __syncthreads();  // the next tile's stage 0 overwrites the buffer and the gate tables
+    }
+}
+
+}  // namespace spx

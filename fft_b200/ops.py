@@ -1,0 +1,216 @@
+"""Torch-facing operators over the C ABI (``include/spectre_mix.h``).
+
+``spectral_mix`` is what the module shells call where the reference has
+``spectre.py:506, :542-553``.  PyTorch is plumbing here -- it owns the device memory
+and the stream; the arithmetic is the sm_100a kernel in ``fft_b200/csrc``.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional
+
+import torch
+
+from . import _lib
+
+_DT = {torch.float32: _lib.F32, torch.bfloat16: _lib.BF16}
+
+
+def _require_cuda(t: torch.Tensor, name: str):
+    if not t.is_cuda:
+        raise RuntimeError(
+            f"fft_b200: `{name}` is on {t.device}; the spectral-mix path is CUDA (sm_100a) only and has no CPU "
+            "fallback. Move the tensors to a B200, or use spectral_mix_host() for host buffers."
+        )
+
+
+def _rows_last_contig(t: torch.Tensor) -> torch.Tensor:
+    return t if t.stride(-1) == 1 or t.size(-1) == 1 else t.contiguous()
+
+
+def _mix_impl(V: torch.Tensor, gate: torch.Tensor, memory: Optional[torch.Tensor], n_fft: int,
+              group_width: int) -> torch.Tensor:
+    _require_cuda(V, "V")
+    if V.dim() != 3:
+        raise ValueError(f"V must be (B, N, C), got {tuple(V.shape)}")
+    if V.dtype not in _DT:
+        raise TypeError(f"V dtype {V.dtype} unsupported (float32 or bfloat16)")
+    B, N, C = V.shape
+    F_half = n_fft // 2 + 1
+    if group_width <= 0 or C % group_width:
+        raise ValueError(f"C={C} is not a multiple of group_width={group_width}")
+    NG = C // group_width
+    if tuple(gate.shape) != (B, NG, F_half):
+        raise ValueError(f"gate must be (B, C/group_width, n_fft/2+1) = {(B, NG, F_half)}, got {tuple(gate.shape)}")
+    if not gate.is_complex():
+        raise TypeError("gate must be complex")
+    gate = gate.to(device=V.device, dtype=torch.complex64).contiguous()
+    V = _rows_last_contig(V)
+    if V.size(-1) == 1 and V.stride(-1) != 1:
+        V = V.contiguous()
+    mem_ptr, mem_stride = None, 0
+    if memory is not None:
+        if tuple(memory.shape) != (F_half, C):
+            raise ValueError(f"memory must be (n_fft/2+1, C) = {(F_half, C)}, got {tuple(memory.shape)}")
+        memory = _rows_last_contig(memory.to(device=V.device, dtype=torch.complex64))
+        mem_ptr, mem_stride = memory.data_ptr(), memory.stride(0)
+    n_out = min(N, n_fft)
+    out = torch.empty((B, n_out, C), dtype=V.dtype, device=V.device)
+    if out.numel() == 0:
+        return out
+    lib = _lib.load()
+    with torch.cuda.device(V.device):
+        stream = torch.cuda.current_stream(V.device).cuda_stream
+        rc = lib.spectre_mix_fwd(
+            V.data_ptr(), _DT[V.dtype], V.stride(0), V.stride(1),
+            gate.data_ptr(), mem_ptr, mem_stride,
+            out.data_ptr(), _DT[out.dtype], out.stride(0), out.stride(1),
+            B, N, n_fft, C, group_width, ctypes.c_void_p(stream),
+        )
+    _lib.check(rc, "spectral_mix")
+    return out
+
+
+@torch.library.custom_op("fft_b200::spectral_mix", mutates_args=(), device_types="cuda")
+def _spectral_mix_op(V: torch.Tensor, gate: torch.Tensor, memory: Optional[torch.Tensor], n_fft: int,
+                     group_width: int) -> torch.Tensor:
+    return _mix_impl(V, gate, memory, n_fft, group_width)
+
+
+@_spectral_mix_op.register_fake
+def _(V, gate, memory, n_fft, group_width):
+    B, N, C = V.shape
+    return V.new_empty((B, min(N, n_fft), C))
+
+
+def _mix_setup_context(ctx, inputs, output):
+    V, gate, memory, n_fft, group_width = inputs
+    ctx.n_fft, ctx.group_width = n_fft, group_width
+    ctx.N = V.shape[1]
+    ctx.has_memory = memory is not None
+    ctx.save_for_backward(V, gate)
+
+
+def _mix_backward(ctx, dY):
+    """Adjoint of the mix, built from the same two kernels.
+
+    y = S . irfft . (G * rfft . P) v  with P = zero-pad to n_fft, S = keep N rows.  The gate acts as a real
+    circular convolution, so  dV = mix(dY, conj(gate))[:N].  d gate needs the two half spectra:
+    dG[b,g,k] = w_k / n * sum_{c in g} conj(Vf[b,k,c]) * dYf[b,k,c]  (w = 1 at DC/Nyquist, 2 elsewhere; the
+    imaginary part at DC/Nyquist is dropped like irfft drops it), and dMemory = w_k / n * sum_b dYf.
+    """
+    V, gate = ctx.saved_tensors
+    n_fft, dg, N = ctx.n_fft, ctx.group_width, ctx.N
+    dV = dgate = dmem = None
+    dY = dY.contiguous()
+    if ctx.needs_input_grad[0]:
+        # dY has min(N, n_fft) rows; the kernel zero-pads them to n_fft itself (that is S^T)
+        full = _mix_impl(dY, torch.conj(gate).resolve_conj(), None, n_fft, dg)
+        dV = full[:, :N]
+        if N > n_fft:  # rows beyond n_fft never reached the transform (spectre.py:506 truncates)
+            dV = torch.nn.functional.pad(dV, (0, 0, 0, N - n_fft))
+    if ctx.needs_input_grad[1] or (ctx.has_memory and ctx.needs_input_grad[2]):
+        dYf = rfft_seq(dY, n_fft)                                    # (B, F, C)
+        F_half = n_fft // 2 + 1
+        w = torch.full((F_half,), 2.0 / n_fft, device=dY.device)
+        w[0] = 1.0 / n_fft
+        if n_fft % 2 == 0:
+            w[-1] = 1.0 / n_fft
+        dYf = dYf * w[None, :, None]
+        edge = torch.zeros(F_half, dtype=torch.bool, device=dY.device)
+        edge[0] = True
+        if n_fft % 2 == 0:
+            edge[-1] = True
+        if ctx.has_memory and ctx.needs_input_grad[2]:
+            dmem = dYf.sum(0)
+            dmem = torch.where(edge[:, None], torch.complex(dmem.real, torch.zeros_like(dmem.real)), dmem)
+        if ctx.needs_input_grad[1]:
+            Vf = rfft_seq(V, n_fft)
+            B, _, C = Vf.shape
+            prod = (torch.conj(Vf) * dYf).view(B, F_half, C // dg, dg).sum(-1)   # (B, F, NG)
+            prod = torch.where(edge[None, :, None], torch.complex(prod.real, torch.zeros_like(prod.real)), prod)
+            dgate = prod.permute(0, 2, 1).contiguous()
+    return dV, dgate, dmem, None, None
+
+
+_spectral_mix_op.register_autograd(_mix_backward, setup_context=_mix_setup_context)
+
+
+def spectral_mix(V: torch.Tensor, gate: torch.Tensor, memory: Optional[torch.Tensor] = None, *,
+                 n_fft: int, group_width: int) -> torch.Tensor:
+    """Fused ``rfft -> gate multiply (+ memory) -> irfft -> [:N]`` over ALL heads in one launch.
+
+    Stands in for ``spectre.py:506, :542-553`` and the head loop of ``:703-718``:
+
+        out[b, n, c] = irfft_n_fft(gate[b, c // group_width, :] * rfft_n_fft(V[b, :, c]) + memory[:, c])[n]
+
+    V       (B, N, C) float32 or bfloat16, CUDA; C = embed_dim (heads are contiguous channel chunks)
+    gate    (B, C // group_width, n_fft//2 + 1) complex64; head h owns rows [h*G, (h+1)*G)
+    memory  optional (n_fft//2 + 1, C) complex64 (row stride may exceed C)
+    returns (B, min(N, n_fft), C) in V's dtype.
+    """
+    _require_cuda(V, "V")
+    return _spectral_mix_op(V, gate, memory, int(n_fft), int(group_width))
+
+
+def rfft_seq(V: torch.Tensor, n_fft: int) -> torch.Tensor:
+    """``torch.fft.rfft(V, n=n_fft, dim=1)`` on the sm_100a kernel (``spectre.py:506`` / ``:777``).
+
+    V (B, N, C) or (N, C); returns complex64 (B, n_fft//2+1, C) (or (n_fft//2+1, C)), contiguous.
+    """
+    _require_cuda(V, "V")
+    squeeze = V.dim() == 2
+    if squeeze:
+        V = V.unsqueeze(0)
+    if V.dtype not in _DT:
+        raise TypeError(f"V dtype {V.dtype} unsupported (float32 or bfloat16)")
+    V = _rows_last_contig(V)
+    B, N, C = V.shape
+    spec = torch.empty((B, n_fft // 2 + 1, C), dtype=torch.complex64, device=V.device)
+    if spec.numel():
+        lib = _lib.load()
+        with torch.cuda.device(V.device):
+            stream = torch.cuda.current_stream(V.device).cuda_stream
+            rc = lib.spectre_rfft_fwd(V.data_ptr(), _DT[V.dtype], V.stride(0), V.stride(1), spec.data_ptr(),
+                                      B, N, n_fft, C, ctypes.c_void_p(stream))
+        _lib.check(rc, "rfft_seq")
+    return spec[0] if squeeze else spec
+
+
+def spectral_mix_host(V: torch.Tensor, gate: torch.Tensor, memory: Optional[torch.Tensor] = None, *,
+                      n_fft: int, group_width: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Same function on HOST tensors through ``spectre_mix_fwd_host`` (copies inside the call).
+
+    This is the entry a non-CUDA caller binds and the one ``bench.py`` times for ``e2e``.  float32 only;
+    pinned tensors copy at full PCIe rate.
+    """
+    if V.is_cuda or gate.is_cuda:
+        raise RuntimeError("spectral_mix_host takes CPU tensors; use spectral_mix for CUDA tensors")
+    V = V.contiguous().float()
+    gate = gate.contiguous().to(torch.complex64)
+    B, N, C = V.shape
+    n_out = min(N, n_fft)
+    if out is None:
+        out = torch.empty((B, n_out, C), dtype=torch.float32)
+    mem_ptr = None
+    if memory is not None:
+        memory = memory.contiguous().to(torch.complex64)
+        mem_ptr = memory.data_ptr()
+    lib = _lib.load()
+    rc = lib.spectre_mix_fwd_host(V.data_ptr(), gate.data_ptr(), mem_ptr, out.data_ptr(), B, N, n_fft, C, group_width)
+    _lib.check(rc, "spectral_mix_host")
+    return out
+
+
+def plan_info(B: int, N: int, n_fft: int, C: int, group_width: int, dtype: torch.dtype = torch.float32,
+              has_memory: bool = False) -> dict:
+    """How the library will run a problem (tile shape, grid, shared memory, algorithmic bytes)."""
+    info = _lib.PlanInfo()
+    rc = _lib.load().spectre_mix_plan(_DT[dtype], _DT[dtype], int(has_memory), B, N, n_fft, C, group_width,
+                                      ctypes.byref(info))
+    _lib.check(rc, "plan_info")
+    return {
+        "n_fft": info.n_fft, "radix": [r for r in info.radix if r > 1], "tile_channels": info.tile_channels,
+        "threads": info.threads, "ctas_per_sm": info.ctas_per_sm, "smem_bytes": info.smem_bytes,
+        "grid": info.grid, "launches": info.launches, "algorithmic_bytes": info.algorithmic_bytes,
+    }

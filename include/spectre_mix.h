@@ -1,0 +1,107 @@
+/* spectre_mix.h -- C ABI of the B200-native Spectre spectral-mix forward path.
+ *
+ * One shared library (fft_b200/_C/libspectre_mix.so), plain pointers and sizes,
+ * no torch types.  Every entry point states which lines of the reference
+ * (/root/reference/spectre.py) it stands in for; the reference itself has no
+ * FFI layer -- it calls torch.fft from Python -- so these are the symbols a
+ * binding (ctypes / pybind / torch.library) attaches to.  See INTEGRATION.md.
+ *
+ * Function computed by the forward entry points, for b < B, n < min(N, n_fft), c < C:
+ *
+ *   out[b, n, c] = irfft_{n_fft}( gate[b, c / group_width, :] * rfft_{n_fft}(V[b, :, c]) + mem[:, c] )[n]
+ *
+ * with rfft zero-padding (N < n_fft) or truncating (N > n_fft) its input, irfft
+ * scaled by 1/n_fft and ignoring the imaginary parts of bin 0 and bin n_fft/2.
+ * All heads of a SpectreMultiHead go in ONE call: C = embed_dim, the gate rows of
+ * head h are rows [h*G, (h+1)*G) of `gate`, group_width = head_dim / G.
+ *
+ * Threading / ownership: the caller owns every buffer; calls are asynchronous on
+ * `stream` (device entry points) and never synchronise the device; per-device
+ * twiddle tables are created on first use under a mutex and are safe to use
+ * from several host threads and under CUDA-graph capture after one warm-up call.
+ * There is no CPU fallback and no cuFFT: an unsupported argument returns an
+ * error code and sets spectre_mix_last_error().
+ */
+#ifndef SPECTRE_MIX_H_
+#define SPECTRE_MIX_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* element types of V and out */
+#define SPECTRE_MIX_F32 0
+#define SPECTRE_MIX_BF16 1
+
+/* return codes (0 = ok; CUDA runtime errors are returned as 1000 + cudaError_t) */
+#define SPECTRE_MIX_OK 0
+#define SPECTRE_MIX_ERR_BAD_ARG 1        /* null pointer, negative size, C % group_width != 0 ... */
+#define SPECTRE_MIX_ERR_UNSUPPORTED 2    /* n_fft not a power of two in [32, 16384], misaligned pointer/stride */
+#define SPECTRE_MIX_ERR_NO_DEVICE 3
+#define SPECTRE_MIX_ERR_CUDA 1000
+
+/* ABI version of this header; bumped on any signature change. */
+int spectre_mix_abi_version(void);
+
+/* Thread-local description of the last non-zero return code on this host thread. */
+const char *spectre_mix_last_error(void);
+
+/* Fused rfft -> gate multiply (+ memory) -> irfft -> [:N] on device buffers.
+ * Replaces spectre.py:506 (rfft), :542-545 (gate broadcast + complex multiply),
+ * :548-549 (memory add), :551 (irfft), :553 (slice) and the per-head loop /
+ * torch.cat of :703-718.
+ *
+ *   v          device, [B][N][C], element stride 1 along C; strides in elements
+ *   gate       device, complex64 [B][C/group_width][n_fft/2+1] contiguous
+ *   mem        device or NULL, complex64 [n_fft/2+1][C], row stride mem_stride (complex elements)
+ *   out        device, [B][min(N,n_fft)][C], element stride 1 along C
+ *   stream     cudaStream_t (NULL = legacy default stream)
+ */
+int spectre_mix_fwd(const void *v, int v_dtype, int64_t v_stride_b, int64_t v_stride_n,
+                    const void *gate, const void *mem, int64_t mem_stride,
+                    void *out, int out_dtype, int64_t out_stride_b, int64_t out_stride_n,
+                    int B, int N, int n_fft, int C, int group_width, void *stream);
+
+/* Same function on HOST buffers (what a non-CUDA host language binds): copies
+ * v/gate/mem to the device in batch chunks, runs the kernel and copies the
+ * result back, overlapping the three on internal streams; returns when `out`
+ * is complete.  Contiguous layouts, fp32 only.  Pinned host memory is used
+ * as-is; pageable memory works but copies slower. */
+int spectre_mix_fwd_host(const float *v, const float *gate, const float *mem, float *out,
+                         int B, int N, int n_fft, int C, int group_width);
+
+/* Forward half only: spec[b, k, c] = rfft_{n_fft}(V[b, :, c])[k], k <= n_fft/2.
+ * Replaces spectre.py:776-777 (PrefixFFTCache.prefill: pad + rfft along dim 0,
+ * B = 1) and is the V_fft of :506.  spec is complex64 [B][n_fft/2+1][C] contiguous. */
+int spectre_rfft_fwd(const void *v, int v_dtype, int64_t v_stride_b, int64_t v_stride_n,
+                     void *spec, int B, int N, int n_fft, int C, void *stream);
+
+/* Tuning / introspection used by bench.py and the tests (not needed by a binding). */
+typedef struct spectre_mix_plan_info {
+    int n_fft;
+    int radix[4];          /* stage radices, product = n_fft, unused = 1 */
+    int tile_channels;     /* channels per CTA tile */
+    int threads;           /* threads per CTA */
+    int ctas_per_sm;       /* resident CTAs per SM the launch is sized for */
+    int smem_bytes;        /* dynamic shared memory per CTA */
+    int grid;              /* CTAs launched for the given problem */
+    int launches;          /* kernel launches per call */
+    int64_t algorithmic_bytes; /* V + out + gate (+ mem) bytes of the call */
+} spectre_mix_plan_info;
+
+int spectre_mix_plan(int v_dtype, int out_dtype, int has_mem, int B, int N, int n_fft, int C,
+                     int group_width, spectre_mix_plan_info *info);
+
+/* Override the tile width (channels per CTA; 0 = automatic).  For experiments only. */
+int spectre_mix_set_tile_channels(int tile_channels);
+
+/* Enable (default) / disable the L2 prefetch of a CTA's next tile.  For experiments only. */
+int spectre_mix_set_prefetch(int enable);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPECTRE_MIX_H_ */

@@ -1,0 +1,75 @@
+"""CPU: the C-ABI library loads and exports every symbol include/spectre_mix.h declares.
+No compute call is made (there is no GPU here)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from conftest import ROOT
+
+
+def _declared_symbols():
+    src = open(os.path.join(ROOT, "include", "spectre_mix.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    names = re.findall(r"\b(spectre_[a-z_0-9]+)\s*\(", src)
+    return sorted(set(names))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    import __graft_entry__ as g
+    from fft_b200 import _lib
+    if not os.path.exists(_lib.LIB_PATH):
+        g.build()
+    return ctypes.CDLL(_lib.LIB_PATH)
+
+
+def test_header_symbols_are_exported(lib):
+    from fft_b200 import _lib
+    names = _declared_symbols()
+    assert names, "no declarations parsed"
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/spectre_mix.h but not exported"
+    assert sorted(_lib.SYMBOLS) == names
+
+
+def test_abi_version_and_error_string(lib):
+    lib.spectre_mix_abi_version.restype = ctypes.c_int
+    assert lib.spectre_mix_abi_version() == 1
+    lib.spectre_mix_last_error.restype = ctypes.c_char_p
+    assert isinstance(lib.spectre_mix_last_error(), bytes)
+
+
+def test_argument_validation_needs_no_gpu():
+    """Bad arguments are rejected before any CUDA call (error codes of include/spectre_mix.h)."""
+    from fft_b200 import _lib
+    lib = _lib.load()
+    # n_fft not a power of two -> UNSUPPORTED (2); C % group_width != 0 -> BAD_ARG (1)
+    rc = lib.spectre_mix_fwd(None, 0, 0, 0, None, None, 0, None, 0, 0, 0, 1, 100, 100, 8, 4, None)
+    assert rc == 2 and b"power of two" in lib.spectre_mix_last_error()
+    rc = lib.spectre_mix_fwd(None, 0, 0, 0, None, None, 0, None, 0, 0, 0, 1, 128, 128, 10, 4, None)
+    assert rc == 1
+    # empty batch is a no-op success even without a device
+    rc = lib.spectre_mix_fwd(None, 0, 0, 0, None, None, 0, None, 0, 0, 0, 0, 128, 128, 8, 4, None)
+    assert rc == 0
+
+
+def test_no_cpu_fallback():
+    """The product path must fail loudly on CPU tensors instead of computing on the host."""
+    import torch
+    import fft_b200
+    V = torch.randn(1, 32, 4)
+    gate = torch.ones(1, 1, 17, dtype=torch.cfloat)
+    with pytest.raises(RuntimeError, match="no CPU"):
+        fft_b200.spectral_mix(V, gate, n_fft=32, group_width=4)
+
+
+def test_product_does_not_import_oracle():
+    """oracle/ is test infrastructure: nothing under fft_b200/ may reference it."""
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "fft_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in txt.replace("no CPU oracle", ""), f"{f} mentions oracle"
+                assert "cufft" not in txt.lower().replace("no cufft", "").replace("not cufft", ""), f"{f} mentions cuFFT"

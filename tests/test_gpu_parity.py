@@ -1,0 +1,295 @@
+"""GPU parity tests: the sm_100a kernel, called through the C ABI, against the CPU oracle.
+
+Tolerances (SURVEY 8c / BASELINE north_star): fp32 rel-L2 <= 1e-5 and max-abs <= 1e-4 * max|y| (the
+north_star's outer bound is 1e-3 relative); bf16 I/O rel-L2 <= 1e-2.  The oracle's own fp32-vs-fp64
+error at n_fft=4096 is rel-L2 1.9e-7.
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden_names, load_golden, max_abs_rel, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+REL_L2_F32 = 1e-5
+MAX_ABS_F32 = 1e-4
+REL_L2_BF16 = 1e-2
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch.device("cuda:0")
+
+
+@pytest.fixture(scope="module")
+def fb():
+    import fft_b200
+    from fft_b200 import _lib
+    _lib.load()  # fail loudly if the CUDA library is missing
+    return fft_b200
+
+
+@pytest.fixture(scope="module")
+def oracle():
+    from oracle import spectre_mix_oracle
+    return spectre_mix_oracle
+
+
+def _check(got, want, rl2=REL_L2_F32, mabs=MAX_ABS_F32):
+    got = got.detach().float().cpu().numpy()
+    want = np.asarray(want, dtype=np.float32)
+    assert got.shape == want.shape, (got.shape, want.shape)
+    assert np.isfinite(got).all()
+    e1, e2 = rel_l2(got, want), max_abs_rel(got, want)
+    assert e1 <= rl2 and e2 <= mabs, f"rel-L2 {e1:.3e} (<= {rl2}), max-abs/max {e2:.3e} (<= {mabs})"
+    return e1
+
+
+# --------------------------------------------------------------------------- reference-generated goldens
+@pytest.mark.parametrize("name", golden_names("mix_"))
+def test_goldens_from_reference(name, fb, dev):
+    g = load_golden(name)
+    mem = None if "mem" not in g else torch.from_numpy(g["mem"]).to(dev)
+    y = fb.spectral_mix(torch.from_numpy(g["V"]).to(dev), torch.from_numpy(g["gate"]).to(dev), mem,
+                        n_fft=int(g["n_fft"]), group_width=int(g["group_width"]))
+    _check(y, g["out"])
+
+
+# --------------------------------------------------------------------------- seeded sweeps against the oracle
+def _rand_case(B, N, n_fft, C, dg, with_mem, seed):
+    gen = torch.Generator().manual_seed(seed)
+    V = torch.randn(B, N, C, generator=gen)
+    gate = torch.randn(B, C // dg, n_fft // 2 + 1, dtype=torch.cfloat, generator=gen)
+    mem = torch.randn(n_fft // 2 + 1, C, dtype=torch.cfloat, generator=gen) / np.sqrt(C) if with_mem else None
+    return V, gate, mem
+
+
+SWEEP = [
+    # B, N, n_fft, C, d_g, mem
+    (2, 32, 32, 16, 4, False),
+    (2, 64, 64, 16, 8, True),
+    (3, 128, 128, 64, 4, True),          # BASELINE config 1 shape (per block: d=64, 4 heads, d_g=4)
+    (2, 256, 256, 32, 16, False),
+    (2, 512, 512, 48, 16, True),
+    (2, 1024, 1024, 64, 16, True),
+    (2, 2048, 2048, 32, 16, False),
+    (2, 4096, 4096, 32, 16, True),
+    (1, 8192, 8192, 16, 16, False),
+    (1, 16384, 16384, 16, 16, True),     # BASELINE config 4 transform length
+    # ragged: zero padding (N < n_fft), truncation (N > n_fft), one row
+    (2, 3000, 4096, 16, 16, False),
+    (2, 1, 1024, 16, 16, True),
+    (2, 700, 512, 16, 16, False),
+    (1, 5000, 4096, 32, 16, True),
+    # channel counts that leave a partial tile, group widths for every element mode
+    (2, 1024, 1024, 24, 8, True),        # QUAD, C not a multiple of the tile
+    (2, 4096, 4096, 40, 8, False),
+    (2, 256, 256, 36, 6, True),          # PAIR (d_g even, not /4)
+    (2, 1024, 1024, 20, 10, False),
+    (2, 256, 256, 15, 3, True),          # REAL (odd group width)
+    (2, 2048, 2048, 7, 1, False),        # one gate per channel
+    (1, 4096, 4096, 768, 16, False),     # Spectre-base row: d=768, 12 heads, G=4
+]
+
+
+@pytest.mark.parametrize("B,N,n_fft,C,dg,with_mem", SWEEP)
+def test_sweep_fp32(B, N, n_fft, C, dg, with_mem, fb, oracle, dev):
+    V, gate, mem = _rand_case(B, N, n_fft, C, dg, with_mem, seed=B * 1000 + N + C)
+    want = oracle.mix_flat(V, gate, n_fft, dg, mem)
+    got = fb.spectral_mix(V.to(dev), gate.to(dev), None if mem is None else mem.to(dev), n_fft=n_fft, group_width=dg)
+    _check(got, want.numpy())
+
+
+@pytest.mark.parametrize("B,N,n_fft,C,dg,with_mem", [
+    (2, 128, 128, 64, 4, True), (2, 1024, 1024, 64, 16, False), (1, 4096, 4096, 96, 16, True),
+    (2, 3000, 4096, 32, 16, False), (2, 256, 256, 36, 6, True), (2, 256, 256, 15, 3, False),
+    (1, 16384, 16384, 16, 16, False),
+])
+def test_sweep_bf16(B, N, n_fft, C, dg, with_mem, fb, oracle, dev):
+    V, gate, mem = _rand_case(B, N, n_fft, C, dg, with_mem, seed=7 + N + C)
+    Vb = V.to(torch.bfloat16)
+    want = oracle.mix_flat(Vb.float(), gate, n_fft, dg, mem)     # oracle on the bf16-rounded input
+    got = fb.spectral_mix(Vb.to(dev), gate.to(dev), None if mem is None else mem.to(dev), n_fft=n_fft, group_width=dg)
+    assert got.dtype == torch.bfloat16
+    _check(got, want.numpy(), rl2=REL_L2_BF16, mabs=2e-2)
+
+
+def test_baseline_config2_full_size(fb, oracle, dev):
+    """BASELINE config 2: batch=32 seq=1024 d=768 fp32, compared element-wise with the oracle."""
+    V, gate, _ = _rand_case(32, 1024, 1024, 768, 16, False, seed=2)
+    want = oracle.mix_flat(V, gate, 1024, 16)
+    got = fb.spectral_mix(V.to(dev), gate.to(dev), n_fft=1024, group_width=16)
+    _check(got, want.numpy())
+
+
+def test_metric_shape_seq4096_d768(fb, oracle, dev):
+    """The metric's shape (seq=4096, d=768, 48 gate groups), B=4, with memory; oracle head loop as the reference runs it."""
+    V, gate, mem = _rand_case(4, 4096, 4096, 768, 16, True, seed=3)
+    want = oracle.mix_head_loop(V, gate, 4096, 12, mem)
+    got = fb.spectral_mix(V.to(dev), gate.to(dev), mem.to(dev), n_fft=4096, group_width=16)
+    _check(got, want.numpy())
+
+
+def test_long_context_16384_d768(fb, oracle, dev):
+    """BASELINE config 4: seq=16384 d=768."""
+    V, gate, _ = _rand_case(1, 16384, 16384, 768, 16, False, seed=4)
+    want = oracle.mix_flat(V, gate, 16384, 16)
+    got = fb.spectral_mix(V.to(dev), gate.to(dev), n_fft=16384, group_width=16)
+    _check(got, want.numpy())
+
+
+# --------------------------------------------------------------------------- size-independent properties at full size
+def test_properties_at_full_size(fb, dev):
+    """B=16, seq=4096, d=768 on the device only: identity gate, linearity, shift, memory-only."""
+    B, N, C, dg = 16, 4096, 768, 16
+    gen = torch.Generator(device=dev).manual_seed(5)
+    V1 = torch.randn(B, N, C, device=dev, generator=gen)
+    V2 = torch.randn(B, N, C, device=dev, generator=gen)
+    F_half = N // 2 + 1
+    ones = torch.ones(B, C // dg, F_half, dtype=torch.cfloat, device=dev)
+    y = fb.spectral_mix(V1, ones, n_fft=N, group_width=dg)
+    assert (y - V1).abs().max().item() < 1e-4 * V1.abs().max().item()          # identity gate -> identity
+    gate = torch.randn(B, C // dg, F_half, dtype=torch.cfloat, device=dev, generator=gen)
+    ya = fb.spectral_mix(V1, gate, n_fft=N, group_width=dg)
+    yb = fb.spectral_mix(V2, gate, n_fft=N, group_width=dg)
+    yab = fb.spectral_mix(2.0 * V1 - 3.0 * V2, gate, n_fft=N, group_width=dg)
+    lin = 2.0 * ya - 3.0 * yb
+    assert (yab - lin).norm().item() <= 2e-6 * lin.norm().item() + 1e-6        # linearity in V
+    s = 37
+    k = torch.arange(F_half, device=dev)
+    shift = torch.exp(-2j * torch.pi * k * s / N).to(torch.cfloat).expand(B, C // dg, -1).contiguous()
+    ys = fb.spectral_mix(V1, shift, n_fft=N, group_width=dg)
+    assert (ys - torch.roll(V1, s, dims=1)).abs().max().item() < 2e-4 * V1.abs().max().item()  # circular shift
+    mem = torch.randn(F_half, C, dtype=torch.cfloat, device=dev, generator=gen)
+    ym = fb.spectral_mix(V1, torch.zeros_like(gate), mem, n_fft=N, group_width=dg)
+    assert (ym - ym[0:1]).abs().max().item() == 0.0                            # zero gate: every row is irfft(memory)
+    # checksum of checksums: sum over time of the output equals DC bin algebra: sum_n y = Re(G0) * sum_n v + Re(M0)
+    g0 = gate[:, :, 0].real.repeat_interleave(dg, dim=1)
+    assert torch.allclose(ya.sum(1), g0 * V1.sum(1), rtol=1e-3, atol=5e-2)
+
+
+def test_kat_impulse_response(fb, dev):
+    """An impulse at n=0 returns irfft(gate) per group (SURVEY section 7 KAT list)."""
+    n_fft, C, dg = 1024, 32, 8
+    V = torch.zeros(1, n_fft, C, device=dev)
+    V[:, 0, :] = 1.0
+    gate = torch.randn(1, C // dg, n_fft // 2 + 1, dtype=torch.cfloat, generator=torch.Generator().manual_seed(9))
+    want = torch.fft.irfft(gate[0], n=n_fft, dim=-1).t().repeat_interleave(dg, dim=1)   # (n_fft, C) on CPU
+    got = fb.spectral_mix(V, gate.to(dev), n_fft=n_fft, group_width=dg)
+    _check(got[0], want.numpy())
+
+
+def test_dc_nyquist_imag_ignored(fb, dev):
+    V, gate, mem = _rand_case(2, 256, 256, 16, 4, True, seed=11)
+    y0 = fb.spectral_mix(V.to(dev), gate.to(dev), mem.to(dev), n_fft=256, group_width=4)
+    gate2, mem2 = gate.clone(), mem.clone()
+    gate2[:, :, 0] = torch.complex(gate[:, :, 0].real, torch.randn(2, 4))
+    mem2[-1] = torch.complex(mem[-1].real, torch.randn(16))
+    mem2[0] = torch.complex(mem[0].real, torch.randn(16))
+    # gate imag at DC multiplies a real bin -> contributes only to the ignored imaginary part
+    y1 = fb.spectral_mix(V.to(dev), gate2.to(dev), mem2.to(dev), n_fft=256, group_width=4)
+    assert torch.equal(y0, y1)
+
+
+# --------------------------------------------------------------------------- layouts
+def test_strided_views(fb, oracle, dev):
+    """V as a channel slice of a wider tensor, memory as a chunk view (row stride > C), as spectre.py:703-707 makes them."""
+    gen = torch.Generator().manual_seed(12)
+    wide = torch.randn(2, 512, 96, generator=gen)
+    memw = torch.randn(257, 96, dtype=torch.cfloat, generator=gen)
+    gate = torch.randn(2, 4, 257, dtype=torch.cfloat, generator=gen)
+    V, mem = wide[:, :, 32:64], memw[:, 32:64]
+    want = oracle.mix_flat(V, gate, 512, 8, mem)
+    dV, dM = wide.to(dev)[:, :, 32:64], memw.to(dev)[:, 32:64]
+    assert not dV.is_contiguous()
+    _check(fb.spectral_mix(dV, gate.to(dev), dM, n_fft=512, group_width=8), want.numpy())
+    # odd channel offset forces the narrower element modes
+    V2 = wide[:, :, 1:33]
+    want2 = oracle.mix_flat(V2, gate, 512, 8)
+    _check(fb.spectral_mix(wide.to(dev)[:, :, 1:33], gate.to(dev), n_fft=512, group_width=8), want2.numpy())
+
+
+def test_empty_and_errors(fb, dev):
+    gate = torch.ones(0, 2, 65, dtype=torch.cfloat, device=dev)
+    y = fb.spectral_mix(torch.zeros(0, 128, 8, device=dev), gate, n_fft=128, group_width=4)
+    assert y.shape == (0, 128, 8)
+    with pytest.raises(RuntimeError, match="power of two"):
+        fb.spectral_mix(torch.zeros(1, 100, 8, device=dev), torch.ones(1, 2, 51, dtype=torch.cfloat, device=dev),
+                        n_fft=100, group_width=4)
+    with pytest.raises(ValueError):
+        fb.spectral_mix(torch.zeros(1, 128, 8, device=dev), torch.ones(1, 2, 64, dtype=torch.cfloat, device=dev),
+                        n_fft=128, group_width=4)
+
+
+# --------------------------------------------------------------------------- the other entry points
+def test_rfft_seq(fb, dev):
+    gen = torch.Generator().manual_seed(13)
+    for (B, N, n_fft, C) in [(2, 128, 128, 16), (1, 200, 256, 32), (2, 1024, 1024, 12), (1, 3000, 4096, 8)]:
+        V = torch.randn(B, N, C, generator=gen)
+        want = torch.fft.rfft(V, n=n_fft, dim=1)
+        got = fb.rfft_seq(V.to(dev), n_fft).cpu()
+        assert got.shape == want.shape
+        assert (got - want).norm() / want.norm() < 1e-6
+    g = load_golden("decode_prefill_n256_d32")          # PrefixFFTCache.prefill of the reference (spectre.py:776-777)
+    got = fb.rfft_seq(torch.from_numpy(g["V"]).to(dev), 256).cpu().numpy()
+    assert rel_l2(got.view(np.float32), g["prefix_fft"].view(np.float32)) < 1e-6
+
+
+def test_host_entry_point(fb, oracle):
+    V, gate, mem = _rand_case(5, 1024, 1024, 64, 16, True, seed=14)
+    want = oracle.mix_flat(V, gate, 1024, 16, mem)
+    got = fb.spectral_mix_host(V, gate, mem, n_fft=1024, group_width=16)
+    _check(got, want.numpy())
+    got2 = fb.spectral_mix_host(V.pin_memory(), gate.pin_memory(), None, n_fft=1024, group_width=16)
+    _check(got2, oracle.mix_flat(V, gate, 1024, 16).numpy())
+
+
+def test_plan_info(fb):
+    info = fb.plan_info(8, 4096, 4096, 768, 16)
+    assert info["n_fft"] == 4096 and np.prod(info["radix"]) == 4096
+    assert info["algorithmic_bytes"] == 8 * 4096 * 768 * 8 + 8 * 48 * 2049 * 8   # 6336.1 B/token
+    assert info["launches"] == 1 and info["grid"] >= 1
+
+
+def test_autograd_matches_oracle(fb, oracle, dev):
+    """Backward of the op against autograd through the oracle's torch.fft path."""
+    for (B, N, n_fft, C, dg) in [(2, 128, 128, 16, 4), (2, 100, 128, 16, 8), (1, 1024, 1024, 16, 16)]:
+        V, gate, mem = _rand_case(B, N, n_fft, C, dg, True, seed=15 + N)
+        w = torch.randn(B, min(N, n_fft), C, generator=torch.Generator().manual_seed(1))
+        Vc, gc, mc = V.clone().requires_grad_(), gate.clone().requires_grad_(), mem.clone().requires_grad_()
+        (oracle.mix_flat(Vc, gc, n_fft, dg, mc) * w).sum().backward()
+        Vg, gg, mg = (V.to(dev).requires_grad_(), gate.to(dev).requires_grad_(), mem.to(dev).requires_grad_())
+        (fb.spectral_mix(Vg, gg, mg, n_fft=n_fft, group_width=dg) * w.to(dev)).sum().backward()
+        assert rel_l2(Vg.grad.cpu().numpy(), Vc.grad.numpy()) < 1e-5
+        assert rel_l2(torch.view_as_real(gg.grad).cpu().numpy(), torch.view_as_real(gc.grad).numpy()) < 1e-5
+        assert rel_l2(torch.view_as_real(mg.grad).cpu().numpy(), torch.view_as_real(mc.grad).numpy()) < 1e-5
+
+
+# --------------------------------------------------------------------------- drop-in module shells
+@pytest.mark.parametrize("name", ["block_d64_h4_n128_mem", "block_d64_h4_n128"])
+def test_block_shell_matches_reference_block(name, fb, dev):
+    """Stock reference SpectreBlock output (golden) vs our shell loaded from the reference's state_dict."""
+    g = load_golden(name)
+    blk = fb.SpectreBlock(64, 4, 128, pooling_type="mean", wavelet_on_rate=0.0, memory_size=int(g["memory_size"]))
+    sd = {k[4:]: torch.from_numpy(v) for k, v in g.items() if k.startswith("sd::")}
+    blk.load_state_dict(sd, strict=True)
+    blk = blk.to(dev).eval()
+    with torch.no_grad():
+        y = blk(torch.from_numpy(g["x"]).to(dev))
+    _check(y, g["y"], rl2=2e-5, mabs=2e-4)   # includes the stock fp32 GEMMs/LayerNorms run on the GPU
+
+
+def test_multihead_matches_per_head_calls(fb, dev):
+    """One fused launch over all heads == the reference's per-head loop (spectre.py:712-718)."""
+    torch.manual_seed(16)
+    mh = fb.SpectreMultiHead(64, 4, 256, pooling_type="mean", wavelet_on_rate=0.0).to(dev).eval()
+    x = torch.randn(2, 200, 64, device=dev)
+    mem = torch.randn(129, 64, dtype=torch.cfloat, device=dev)
+    with torch.no_grad():
+        fused = mh(x, memory_fft=mem)
+        per_head = [h(c, None, return_q_pool=True, memory_fft=m)[0]
+                    for h, c, m in zip(mh.heads, torch.chunk(x, 4, -1), torch.chunk(mem, 4, -1))]
+        loop = mh.out_proj(torch.cat(per_head, dim=-1))
+    assert (fused - loop).norm() / loop.norm() < 1e-5
