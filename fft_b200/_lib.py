@@ -25,6 +25,8 @@ SYMBOLS = (
     "spectre_mix_plan",
     "spectre_mix_set_tile_channels",
     "spectre_mix_set_prefetch",
+    "spectre_mix_set_tma",
+    "spectre_mix_set_timeline",
 )
 
 
@@ -78,6 +80,10 @@ def load():
         lib.spectre_mix_set_tile_channels.argtypes = [i32]
         lib.spectre_mix_set_prefetch.restype = i32
         lib.spectre_mix_set_prefetch.argtypes = [i32]
+        lib.spectre_mix_set_tma.restype = i32
+        lib.spectre_mix_set_tma.argtypes = [i32]
+        lib.spectre_mix_set_timeline.restype = i32
+        lib.spectre_mix_set_timeline.argtypes = [vp]
         _lib = lib
     return _lib
 

@@ -3,6 +3,7 @@
 // Host-side counterpart of the reference's call sites spectre.py:506, :542-553
 // (forward mix) and :776-777 (prefill rfft).  No torch types, no cuFFT, no CPU
 // fallback: anything this file cannot run returns an error code.
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdarg.h>
@@ -40,7 +41,9 @@ int cuda_fail(cudaError_t e, const char *what) {
 }
 
 int g_tile_channels_override = 0;
-int g_prefetch = 1;
+int g_prefetch = 0;   // L2 prefetch of the next tile: measured neutral-to-harmful so far (profiles/), off by default
+int g_use_tma = 1;
+unsigned long long *g_timeline = nullptr;
 
 // ---------------------------------------------------------------- kernel registry
 const std::vector<KernelEntry> &registry() {
@@ -156,7 +159,8 @@ int pick_mode(int dtype, int group_width, const void *v, long long v_sb, long lo
     return spx::MODE_REAL;
 }
 
-int choose(const DeviceState &st, int n_fft, int dtype, int mode_max, int C, int group_width, Choice *out) {
+int choose(const DeviceState &st, int n_fft, int dtype, int mode_max, int C, int group_width, Choice *out,
+           bool no_gate = false) {
     const std::vector<KernelEntry> &reg = registry();
     // candidates in registry order (first = default) for the widest mode that has any variant
     for (int mode = mode_max; mode <= spx::MODE_REAL; ++mode) {
@@ -172,7 +176,8 @@ int choose(const DeviceState &st, int n_fft, int dtype, int mode_max, int C, int
             if (group_width % tw == 0) gt = 1;
             else if (tw % group_width == 0) gt = tw / group_width;
             else gt = (tw + group_width - 1) / group_width + 1;
-            const size_t sm = k.smem_bytes(gt);
+            if (no_gate) gt = 0;
+            const size_t sm = k.smem_bytes(gt, false);
             if ((int)sm > st.max_smem_optin) continue;
             const int ce = C / ch;
             Choice c;
@@ -205,13 +210,52 @@ int check_common(int B, int N, int n_fft, int C, int group_width) {
     return 0;
 }
 
-int occupancy_of(DeviceState &st, const Choice &c, bool has_mem) {
-    auto key = std::make_pair(c.k, c.gate_tables * 2 + (has_mem ? 1 : 0));
+int occupancy_of(DeviceState &st, const Choice &c, bool has_mem, bool tma) {
+    auto key = std::make_pair(c.k, c.gate_tables * 4 + (has_mem ? 1 : 0) + (tma ? 2 : 0));
     auto it = st.occupancy.find(key);
     if (it != st.occupancy.end()) return it->second;
-    int occ = c.k->occupancy(c.gate_tables, has_mem);
+    int occ = c.k->occupancy(c.gate_tables, has_mem, tma);
     st.occupancy[key] = occ;
     return occ;
+}
+
+// ---------------------------------------------------------------- TMA descriptor for V ([B][rows][C], channels contiguous)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = [] {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess) {
+            cudaGetLastError();
+            p = nullptr;
+        }
+        return reinterpret_cast<EncodeTiledFn>(p);
+    }();
+    return fn;
+}
+
+// true when V can be described to the TMA unit: 16-byte aligned base and strides, extents within 32 bits
+bool tma_layout_ok(const void *v, int dtype, long long v_sb, long long v_sn) {
+    const long long es = dtype == SPECTRE_MIX_F32 ? 4 : 2;
+    return aligned(v, 16) && (v_sb * es) % 16 == 0 && (v_sn * es) % 16 == 0 && v_sn > 0 && v_sb > 0;
+}
+
+bool make_v_tensor_map(CUtensorMap *tm, const void *v, int dtype, long long v_sb, long long v_sn, int B, int rows, int C,
+                       int box_rows, int tile_channels) {
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc) return false;
+    const cuuint64_t es = dtype == SPECTRE_MIX_F32 ? 4 : 2;
+    cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)rows, (cuuint64_t)B};
+    cuuint64_t strides[2] = {(cuuint64_t)v_sn * es, (cuuint64_t)v_sb * es};
+    cuuint32_t box[3] = {(cuuint32_t)tile_channels, (cuuint32_t)box_rows, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(tm, dtype == SPECTRE_MIX_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3,
+                     const_cast<void *>(v), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
 }
 
 }  // namespace
@@ -230,6 +274,16 @@ int spectre_mix_set_tile_channels(int tile_channels) {
 
 int spectre_mix_set_prefetch(int enable) {
     g_prefetch = enable ? 1 : 0;
+    return 0;
+}
+
+int spectre_mix_set_timeline(void *device_buffer) {
+    g_timeline = reinterpret_cast<unsigned long long *>(device_buffer);
+    return 0;
+}
+
+int spectre_mix_set_tma(int enable) {
+    g_use_tma = enable ? 1 : 0;
     return 0;
 }
 
@@ -281,10 +335,20 @@ int spectre_mix_fwd(const void *v, int v_dtype, int64_t v_stride_b, int64_t v_st
     p.gate_tables = c.gate_tables;
     p.inv_n = 1.0f / (float)n_fft;
     p.prefetch = g_prefetch;
+    p.timeline = g_timeline;
 
-    const int occ = std::max(1, occupancy_of(*st, c, mem != nullptr));
+    // TMA-fed variant when V's layout can be described to the TMA unit; otherwise direct 128-bit global loads
+    alignas(64) CUtensorMap tmap, tmap_out;
+    const int tile_ch = mode_channels(c.k->mode) * c.k->ncol;
+    bool tma = g_use_tma && c.k->tma_ok && (int)c.k->smem_bytes(c.gate_tables, true) <= st->max_smem_optin &&
+               tma_layout_ok(v, v_dtype, v_stride_b, v_stride_n) && tma_layout_ok(out, out_dtype, out_stride_b, out_stride_n) &&
+               make_v_tensor_map(&tmap, v, v_dtype, v_stride_b, v_stride_n, B, n_io, C, std::min(n_fft, spx::kTmaBoxRows),
+                                 tile_ch) &&
+               make_v_tensor_map(&tmap_out, out, out_dtype, out_stride_b, out_stride_n, B, n_io, C, c.k->out_box_rows, tile_ch);
+    const int occ = std::max(1, occupancy_of(*st, c, mem != nullptr, tma));
     const int grid = std::min(p.num_tiles, st->sm_count * occ);
-    cudaError_t e = c.k->launch(p, grid, mem != nullptr, reinterpret_cast<cudaStream_t>(stream));
+    cudaError_t e = c.k->launch(p, grid, mem != nullptr, tma ? &tmap : nullptr, tma ? &tmap_out : nullptr,
+                                reinterpret_cast<cudaStream_t>(stream));
     if (e != cudaSuccess) return cuda_fail(e, "kernel launch");
     return 0;
 }
@@ -305,8 +369,8 @@ int spectre_mix_plan(int v_dtype, int out_dtype, int has_mem, int B, int N, int 
     for (int i = 0; i < 4; ++i) info->radix[i] = c.k->radix[i];
     info->tile_channels = mode_channels(c.k->mode) * c.k->ncol;
     info->threads = c.k->threads;
-    info->ctas_per_sm = std::max(1, occupancy_of(*st, c, has_mem != 0));
-    info->smem_bytes = (int)c.smem;
+    info->ctas_per_sm = std::max(1, occupancy_of(*st, c, has_mem != 0, g_use_tma && c.k->tma_ok));
+    info->smem_bytes = (int)c.k->smem_bytes(c.gate_tables, g_use_tma && c.k->tma_ok);
     info->grid = std::min(B * c.tiles_per_row, st->sm_count * info->ctas_per_sm);
     info->launches = 1;
     info->algorithmic_bytes = algorithmic_bytes(v_dtype, has_mem != 0, B, N, n_fft, C, group_width);
@@ -325,7 +389,7 @@ int spectre_rfft_fwd(const void *v, int v_dtype, int64_t v_stride_b, int64_t v_s
     DeviceState *st = nullptr;
     if (int rc = get_device_state(&st, nullptr)) return rc;
     Choice c;
-    if (int rc = choose(*st, n_fft, v_dtype, spx::MODE_REAL, C, 1, &c)) return rc;
+    if (int rc = choose(*st, n_fft, v_dtype, spx::MODE_REAL, C, 1, &c, /*no_gate=*/true)) return rc;
     if (!c.k->launch_rfft) return fail(SPECTRE_MIX_ERR_UNSUPPORTED, "internal: no rfft variant");
     const float2 *tw = nullptr;
     if (int rc = get_twiddles(*st, *c.k, &tw)) return rc;

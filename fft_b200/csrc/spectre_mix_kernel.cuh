@@ -30,6 +30,7 @@
 //     being transformed (L2 is the landing buffer -- a 4096x8 fp32 tile fills
 //     shared memory on its own).
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
 #include <stdint.h>
@@ -50,7 +51,16 @@ struct MixParams {
     int gate_tables;      // gate groups a tile may touch (smem sized for this many)
     float inv_n;
     int prefetch;         // 1: prefetch the CTA's next tile into L2 while this one is transformed
+    unsigned long long *timeline;  // optional: per-CTA phase timestamps (ns) for tools/timeline.py, else nullptr
 };
+
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+constexpr int kTimelineSlots = 8;     // timestamps per tile
+constexpr int kTimelineTiles = 8;     // tiles recorded per CTA
 
 // ------------------------------------------------------------------ packed / scalar lanes
 __device__ __forceinline__ float2 vadd(float2 a, float2 b) { return __fadd2_rn(a, b); }
@@ -193,6 +203,19 @@ struct Plan {
 
 __host__ __device__ constexpr int cmax(int a, int b) { return a > b ? a : b; }
 
+// Which stages keep their twiddles in shared memory: all of them while the tables fit beside the tile; from
+// n_fft = 8192 the (largest) stage-0 table is read through L2 instead, at 16384 every table is.
+template <class PL>
+struct TwPolicy {
+    static constexpr int FROM = (PL::N >= 16384) ? (PL::NS - 1) : ((PL::N >= 8192) ? 1 : 0);
+    static constexpr int SMEM_N = PL::TWN - PL::TWOFF(FROM);   // entries held in shared memory
+};
+template <class PL, int S_>
+__device__ __forceinline__ float2 tw_get(const float2 *tw_s, const float2 *tw_g, int idx) {
+    if constexpr (S_ >= TwPolicy<PL>::FROM) return tw_s[PL::TWOFF(S_) - PL::TWOFF(TwPolicy<PL>::FROM) + idx];
+    else return __ldg(tw_g + PL::TWOFF(S_) + idx);
+}
+
 // ------------------------------------------------------------------ element traits per mode
 template <int MODE>
 struct Elem;
@@ -295,9 +318,20 @@ struct Smem {
     static constexpr int SKEW = cmax(1, E::WAVE / NCOL);
     static constexpr int CS = PL::NPAD + SKEW;                 // column stride in elements
     static constexpr size_t data_bytes = sizeof(typename E::S) * (size_t)CS * NCOL;
-    static constexpr size_t tw_bytes = ((sizeof(float2) * (size_t)PL::TWN + 15) / 16) * 16;
+    static constexpr size_t tw_bytes = ((sizeof(float2) * (size_t)TwPolicy<PL>::SMEM_N + 15) / 16) * 16;
     static constexpr size_t gate_bytes_one = ((sizeof(float2) * (size_t)PL::GPAD + 15) / 16) * 16;
-    static constexpr size_t bytes(int gate_tables) { return data_bytes + tw_bytes + gate_bytes_one * (size_t)gate_tables; }
+    // TMA variant: 3 mbarriers + two output staging buffers of STG_MB stage-0 row blocks each
+    __host__ __device__ static constexpr int cmin_(int a, int b) { return a < b ? a : b; }
+    // stage-0 row blocks (L(0) rows each) per staging round: at least one TMA box (256 rows) when the tile has that many
+    static constexpr int STG_MB = cmin_(PL::R(0), cmax(1, 256 / PL::L(0)) * (PL::N >= 4096 ? 2 : 1));
+    static constexpr int STG_ROWS = STG_MB * PL::L(0);                       // rows per staging round
+    static constexpr int OUT_BOX_ROWS = cmin_(STG_ROWS, 256);                // rows per TMA store
+    __host__ __device__ static constexpr size_t stg_bytes(size_t row_bytes) { return (size_t)STG_ROWS * row_bytes; }
+    static constexpr size_t bar_bytes = 128;
+    __host__ __device__ static constexpr size_t base_bytes(int gate_tables) { return data_bytes + tw_bytes + gate_bytes_one * (size_t)gate_tables; }
+    static constexpr size_t bytes(int gate_tables, bool tma = false, size_t row_bytes = 0) {
+        return ((base_bytes(gate_tables) + 127) / 128) * 128 + bar_bytes + (tma ? 2 * stg_bytes(row_bytes) : 0);
+    }
 };
 
 // stage-s butterfly id -> frequency digits: k_low = sum_{i < NS-1} q_i P(i), given Q of the last stage
@@ -318,7 +352,7 @@ __device__ __forceinline__ int klow_of(int Q) {
 // Butterfly bf = Q * L + u of a column works on elements Q*(R*L) + m*L + u, m < R, and leaves output
 // digit q in the slot of input m = q, so no pass ever moves data between slots.
 template <class PL, int MODE, int NCOL, int NT, int S_>
-__device__ __forceinline__ void fwd_inner_pass(typename Elem<MODE>::S *buf, const float2 *tw, int tid) {
+__device__ __forceinline__ void fwd_inner_pass(typename Elem<MODE>::S *buf, const float2 *tw, const float2 *twg, int tid) {
     using E = Elem<MODE>;
     using V = typename E::V;
     constexpr int R = PL::R(S_), L = PL::L(S_), NBF = PL::N / R, ITEMS = NCOL * NBF;
@@ -333,10 +367,9 @@ __device__ __forceinline__ void fwd_inner_pass(typename Elem<MODE>::S *buf, cons
 #pragma unroll
         for (int m = 0; m < R; ++m) x[m] = E::unpack(cb[m * L + ((m * L) >> 4)]);
         Dft<R, V>::run(x);
-        const float2 *tws = tw + PL::TWOFF(S_) + u;
 #pragma unroll
         for (int q = 1; q < R; ++q) {
-            const float2 wq = tws[(q - 1) * L];
+            const float2 wq = tw_get<PL, S_>(tw, twg, (q - 1) * L + u);
             x[q] = cmul(x[q], wq.x, wq.y);
         }
 #pragma unroll
@@ -346,7 +379,7 @@ __device__ __forceinline__ void fwd_inner_pass(typename Elem<MODE>::S *buf, cons
 
 // inverse of the above: conj-twiddle then inverse butterfly, done as forward arithmetic on (im, re)
 template <class PL, int MODE, int NCOL, int NT, int S_>
-__device__ __forceinline__ void inv_inner_pass(typename Elem<MODE>::S *buf, const float2 *tw, int tid) {
+__device__ __forceinline__ void inv_inner_pass(typename Elem<MODE>::S *buf, const float2 *tw, const float2 *twg, int tid) {
     using E = Elem<MODE>;
     using V = typename E::V;
     constexpr int R = PL::R(S_), L = PL::L(S_), NBF = PL::N / R, ITEMS = NCOL * NBF;
@@ -356,13 +389,12 @@ __device__ __forceinline__ void inv_inner_pass(typename Elem<MODE>::S *buf, cons
         const int Q = bf / L, u = bf - Q * L;
         const int e0 = Q * (R * L) + u;
         typename E::S *cb = buf + col * CS + e0 + (e0 >> 4);
-        const float2 *tws = tw + PL::TWOFF(S_) + u;
         Cx<V> x[R];
 #pragma unroll
         for (int q = 0; q < R; ++q) {
             x[q] = cswap(E::unpack(cb[q * L + ((q * L) >> 4)]));
             if (q > 0) {
-                const float2 wq = tws[(q - 1) * L];
+                const float2 wq = tw_get<PL, S_>(tw, twg, (q - 1) * L + u);
                 x[q] = cmul(x[q], wq.x, wq.y);
             }
         }
@@ -395,10 +427,115 @@ __device__ __forceinline__ void mem_add(Cx<float> &x, const float2 *mp, float in
     }
 }
 
+// ------------------------------------------------------------------ TMA / mbarrier primitives (sm_90+ PTX)
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// box {channels, rows, 1} of the [B][rows][C] tensor -> dense [rows][channels] in shared memory
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const void *tmap, int c, int row, int b, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+        ::"r"(dst), "l"(tmap), "r"(c), "r"(row), "r"(b), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_3d(const void *tmap, int c, int row, int b) {
+    asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(tmap), "r"(c), "r"(row), "r"(b)
+                 : "memory");
+}
+
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// dense [rows][channels] in shared memory -> box {channels, rows, 1} of the [B][rows][C] output (clipped at the edges)
+__device__ __forceinline__ void tma_store_3d(const void *tmap, uint32_t src, int c, int row, int b) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%1, %2, %3}], [%4];" ::"l"(tmap), "r"(c),
+                 "r"(row), "r"(b), "r"(src)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int PENDING>
+__device__ __forceinline__ void tma_wait_read() {
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(PENDING) : "memory");
+}
+__device__ __forceinline__ void tma_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+// landing-buffer element (one tile element as TMA delivers it: CH consecutive channels of one row)
+template <int MODE, class IO>
+struct Lin;
+template <>
+struct Lin<MODE_QUAD, float> {
+    using T = float4;
+    static __device__ __forceinline__ Cx<float2> get(const T &f) { return {make_float2(f.x, f.y), make_float2(f.z, f.w)}; }
+    static __device__ __forceinline__ T put(const Cx<float2> &c) { return make_float4(c.re.x, c.re.y, c.im.x, c.im.y); }
+};
+template <>
+struct Lin<MODE_QUAD, __nv_bfloat16> {
+    using T = uint2;
+    static __device__ __forceinline__ Cx<float2> get(const T &r) {
+        __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162 *>(&r.x), b = *reinterpret_cast<const __nv_bfloat162 *>(&r.y);
+        return {__bfloat1622float2(a), __bfloat1622float2(b)};
+    }
+    static __device__ __forceinline__ T put(const Cx<float2> &c) {
+        __nv_bfloat162 a = __float22bfloat162_rn(c.re), b = __float22bfloat162_rn(c.im);
+        uint2 r;
+        r.x = *reinterpret_cast<unsigned *>(&a);
+        r.y = *reinterpret_cast<unsigned *>(&b);
+        return r;
+    }
+};
+template <int MODE, class IO>
+struct Lin {  // PAIR / REAL never use the TMA path
+    using T = float2;
+    static __device__ __forceinline__ Cx<float> get(const T &f) { return {f.x, f.y}; }
+    static __device__ __forceinline__ T put(const Cx<float> &c) { return make_float2(c.re, c.im); }
+};
+
+constexpr int kTmaBoxRows = 256;
+
+// gate row -> registers (all loads in flight), registers -> padded shared table
+template <int N, int NT, int GK>
+__device__ __forceinline__ void gate_fetch(float2 (&gv)[GK], const float2 *gp, int tid) {
+#pragma unroll
+    for (int j = 0; j < GK; ++j) {
+        const int k = tid + j * NT;
+        gv[j] = (k <= N / 2) ? __ldg(gp + k) : make_float2(0.f, 0.f);
+    }
+}
+template <int N, int NT, int GK>
+__device__ __forceinline__ void gate_put(float2 *gs, const float2 (&gv)[GK], int tid, float inv_n) {
+#pragma unroll
+    for (int j = 0; j < GK; ++j) {
+        const int k = tid + j * NT;
+        if (k <= N / 2) {
+            const float im = (k == 0 || k == N / 2) ? 0.f : gv[j].y * inv_n;
+            gs[k + (k >> 4)] = make_float2(gv[j].x * inv_n, im);
+        }
+    }
+}
+
 // ------------------------------------------------------------------ the kernel
-// KIND 0: full mix (rfft -> gate (+mem) -> irfft);  KIND 1: rfft only (half spectrum out, MODE_PAIR/REAL... see api)
-template <class PL, int MODE, int NCOL, int NT, int MINB, class TIN, class TOUT, bool HAS_MEM, bool RFFT_ONLY = false>
-__global__ void __launch_bounds__(NT, MINB) spectre_mix_kernel(const MixParams p) {
+// One persistent CTA per resident slot; each loop iteration transforms one tile = all n_fft rows of NCOL
+// elements (CH channels each) of one batch row.  RFFT_ONLY: stop after the forward half and write the half
+// spectrum.  TMA_IN: the tile is brought into shared memory by TMA (cp.async.bulk.tensor) and the CTA's next
+// tile is prefetched into L2 by the TMA unit; otherwise stage 0 loads straight from global into registers.
+template <class PL, int MODE, int NCOL, int NT, int MINB, class TIN, class TOUT, bool HAS_MEM, bool RFFT_ONLY = false,
+          bool TMA_IN = false>
+__global__ void __launch_bounds__(NT, MINB)
+    spectre_mix_kernel(const MixParams p, const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_out) {
     using E = Elem<MODE>;
     using V = typename E::V;
     using S = typename E::S;
@@ -406,87 +543,166 @@ __global__ void __launch_bounds__(NT, MINB) spectre_mix_kernel(const MixParams p
     constexpr int N = PL::N, NS = PL::NS, CH = E::CH, CS = SM::CS;
     constexpr int RL = PL::R(NS - 1);       // radix of the last stage (fused middle pass)
     constexpr int PLAST = PL::P(NS - 1);    // = N / RL
+    constexpr int R0 = PL::R(0), L0 = PL::L(0);
+    constexpr int ITEMS0 = NCOL * L0;                       // stage-0 butterflies per tile
+    constexpr int ITERS0 = (ITEMS0 + NT - 1) / NT;          // per thread
+    static_assert(!TMA_IN || (MODE == MODE_QUAD && !RFFT_ONLY), "TMA path is built for the packed mix kernel");
+    // stage NS-2 and the middle pass both have radix 16 and >= 32 butterflies per column, items map to threads
+    // identically in both (w = tid + k NT): their exchange stays inside a warp
+    constexpr bool kWarpLocal = (NS >= 3) && (PL::R(NS - 1) == 16) && (PL::R(NS - 2) == 16) && (NT % 32 == 0) &&
+                                ((NCOL * (N / 16)) % NT == 0 || NT % (NCOL * (N / 16)) == 0) && ((N / 16) % 32 == 0);
 
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
     S *buf = reinterpret_cast<S *>(smem_raw);
     float2 *tw = reinterpret_cast<float2 *>(smem_raw + SM::data_bytes);
     float2 *gate_s = reinterpret_cast<float2 *>(smem_raw + SM::data_bytes + SM::tw_bytes);
     constexpr int GS = (int)(SM::gate_bytes_one / sizeof(float2));
+    // mbarriers (tile landed, staging buffer 0/1 free) and the output staging buffers live after the gate tables
+    const size_t bar_off = ((SM::base_bytes(p.gate_tables) + 127) / 128) * 128;
+    const uint32_t bar = smem_u32(smem_raw + bar_off);
+    const uint32_t freeb = bar + 16;
+    unsigned char *stg = smem_raw + bar_off + SM::bar_bytes;
 
     const int tid = threadIdx.x;
-    for (int i = tid; i < PL::TWN; i += NT) tw[i] = p.tw[i];
+    for (int i = tid; i < TwPolicy<PL>::SMEM_N; i += NT) tw[i] = p.tw[PL::TWOFF(TwPolicy<PL>::FROM) + i];
     // first __syncthreads of the tile loop publishes the table
 
+    constexpr int GK = (N / 2 + 1 + NT - 1) / NT;   // gate entries per thread
+    const bool gate_early = (p.gate_tables == 1);   // one table per tile: fetch the next tile's while this one finishes
     const TIN *vbase = reinterpret_cast<const TIN *>(p.v);
     TOUT *obase = reinterpret_cast<TOUT *>(p.out);
     const int CE = p.C / CH;  // elements per row
+
+    using LT = typename Lin<MODE, TIN>::T;
+    constexpr int BOXR = N < kTmaBoxRows ? N : kTmaBoxRows;
+    constexpr uint32_t ROWB = (uint32_t)(sizeof(LT) * NCOL);        // landed bytes per row
+    auto issue_tile_load = [&](int t) {                              // one thread
+        const int tb = t / p.tiles_per_row;
+        const int tc = (t - tb * p.tiles_per_row) * NCOL * CH;
+        mbar_expect_tx(bar, ROWB * N);
+#pragma unroll 1
+        for (int r0 = 0; r0 < N; r0 += BOXR) tma_load_3d(smem_u32(smem_raw) + r0 * ROWB, &tmap, tc, r0, tb, bar);
+    };
+    auto prefetch_tile = [&](int t) {                                // one thread; rows past n_in need no traffic
+        const int tb = t / p.tiles_per_row;
+        const int tc = (t - tb * p.tiles_per_row) * NCOL * CH;
+#pragma unroll 1
+        for (int r0 = 0; r0 < p.n_in; r0 += BOXR) tma_prefetch_3d(&tmap, tc, r0, tb);
+    };
+    if constexpr (TMA_IN) {
+        if (tid == 0) {
+            mbar_init(bar, 1);
+            mbar_init(freeb, 1);
+            mbar_init(freeb + 8, 1);
+            if ((int)blockIdx.x < p.num_tiles) issue_tile_load(blockIdx.x);
+        }
+    }
+    uint32_t parity = 0;
+    int tl_tile = 0;
+#define SPX_MARK(slot)                                                                                   \
+    if (p.timeline && tid == 0 && tl_tile < kTimelineTiles)                                              \
+        p.timeline[((size_t)blockIdx.x * kTimelineTiles + tl_tile) * kTimelineSlots + (slot)] = globaltimer_ns();
+    uint32_t rnd = 0;   // output staging rounds issued so far (buffer = rnd & 1)
 
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         const int b = tile / p.tiles_per_row;
         const int ce0 = (tile - b * p.tiles_per_row) * NCOL;  // first element column of the tile
         const int c0 = ce0 * CH;
         const int g0 = c0 / p.group_width;
+        const bool full_tile = (ce0 + NCOL <= CE) && (p.n_in == N);
+        SPX_MARK(0)
 
-        // ---- stage the gate tables of this tile (scaled by 1/n_fft, imag(DC)=imag(Nyquist)=0)
-        for (int t = 0; t < p.gate_tables; ++t) {
-            const int g = g0 + t;
-            if (g < p.NG) {
-                const float2 *gp = p.gate + ((long long)b * p.NG + g) * (N / 2 + 1);
-                for (int k = tid; k <= N / 2; k += NT) {
-                    float2 gv = __ldg(gp + k);
-                    gv.x *= p.inv_n;
-                    gv.y = (k == 0 || k == N / 2) ? 0.f : gv.y * p.inv_n;
-                    gate_s[t * GS + k + (k >> 4)] = gv;
+        // ---- stage the gate tables of this tile (scaled by 1/n_fft, imag(DC)=imag(Nyquist)=0).  With one table per
+        // tile this was already done while the previous tile finished (see below); else do it here.
+        if constexpr (!RFFT_ONLY) {
+            if (!gate_early || tile == (int)blockIdx.x) {
+                for (int t = 0; t < p.gate_tables; ++t) {
+                    const int g = g0 + t;
+                    if (g < p.NG) {
+                        float2 gv[GK];
+                        gate_fetch<N, NT, GK>(gv, p.gate + ((long long)b * p.NG + g) * (N / 2 + 1), tid);
+                        gate_put<N, NT, GK>(gate_s + t * GS, gv, tid, p.inv_n);
+                    }
                 }
             }
         }
 
-        // ---- forward stage 0: global -> butterfly -> twiddle -> smem
+        // ---- forward stage 0: (TMA landing buffer | global) -> butterfly -> twiddle -> padded column layout
         {
-            constexpr int R = PL::R(0), L = PL::L(0);
-            constexpr int ITEMS = NCOL * L;
-            const TIN *vb = vbase + (long long)b * p.v_sb + c0;
-            const int next_tile = tile + gridDim.x;
-            const TIN *vnext = nullptr;
-            if (p.prefetch && next_tile < p.num_tiles) {
-                const int nb = next_tile / p.tiles_per_row;
-                vnext = vbase + (long long)nb * p.v_sb + (long long)(next_tile - nb * p.tiles_per_row) * NCOL * CH;
-            }
-            for (int w = tid; w < ITEMS; w += NT) {
-                const int col = w % NCOL, u = w / NCOL;
-                const bool colok = (ce0 + col) < CE;
-                Cx<V> x[R];
+            Cx<V> x0[ITERS0][R0];
+            if constexpr (TMA_IN) {
+                mbar_wait(bar, parity);
+                parity ^= 1;
+                SPX_MARK(1)
+                // this tile is on chip: let the TMA unit pull the next one into L2 while we transform
+                if (p.prefetch && tid == 0 && tile + (int)gridDim.x < p.num_tiles) prefetch_tile(tile + gridDim.x);
+                const LT *lin = reinterpret_cast<const LT *>(smem_raw);
 #pragma unroll
-                for (int m = 0; m < R; ++m) {
-                    const int row = u + m * L;
-                    if (colok && row < p.n_in) x[m] = GIO<MODE, TIN>::load(vb + (long long)row * p.v_sn + col * CH);
-                    else x[m] = {vzero(V()), vzero(V())};
-                }
-                if (vnext != nullptr && colok) {
+                for (int it = 0; it < ITERS0; ++it) {
+                    const int w = tid + it * NT;
+                    const int col = w % NCOL, u = w / NCOL;
+                    if (ITEMS0 % NT == 0 || w < ITEMS0) {
 #pragma unroll
-                    for (int m = 0; m < R; ++m) {
-                        const int row = u + m * L;
-                        if (row < p.n_in) prefetch_l2(vnext + (long long)row * p.v_sn + col * CH);
+                        for (int m = 0; m < R0; ++m) x0[it][m] = Lin<MODE, TIN>::get(lin[(u + m * L0) * NCOL + col]);
                     }
                 }
-                Dft<R, V>::run(x);
-                const float2 *tws = tw + PL::TWOFF(0) + u;
+                __syncthreads();   // every landed element is in registers: the buffer may be rewritten in place
+            } else {
+                const TIN *vb = vbase + (long long)b * p.v_sb + c0;
 #pragma unroll
-                for (int q = 1; q < R; ++q) {
-                    const float2 wq = tws[(q - 1) * L];
-                    x[q] = cmul(x[q], wq.x, wq.y);
+                for (int it = 0; it < ITERS0; ++it) {
+                    const int w = tid + it * NT;
+                    const int col = w % NCOL, u = w / NCOL;
+                    if (ITEMS0 % NT == 0 || w < ITEMS0) {
+                        const TIN *vp = vb + (long long)u * p.v_sn + col * CH;
+                        if (full_tile) {
+#pragma unroll
+                            for (int m = 0; m < R0; ++m) x0[it][m] = GIO<MODE, TIN>::load(vp + (long long)(m * L0) * p.v_sn);
+                        } else {
+                            // ragged tile: read a clamped (always valid) address, then select; the select reads the
+                            // loaded register, so the loads still overlap (a predicated load + zero fill would not)
+                            const bool colok = (ce0 + col) < CE;
+                            const TIN *vq = vb + (colok ? col * CH : 0);
+#pragma unroll
+                            for (int m = 0; m < R0; ++m) {
+                                const int row = u + m * L0;
+                                const bool ok = colok && row < p.n_in;
+                                Cx<V> t = GIO<MODE, TIN>::load(vq + (long long)(ok ? row : 0) * p.v_sn);
+                                if (!ok) t = {vzero(V()), vzero(V())};
+                                x0[it][m] = t;
+                            }
+                        }
+                    }
                 }
-                S *cb = buf + col * CS + u + (u >> 4);
+            }
 #pragma unroll
-                for (int q = 0; q < R; ++q) cb[q * L + ((q * L) >> 4)] = E::pack(x[q]);
+            for (int it = 0; it < ITERS0; ++it) {
+                const int w = tid + it * NT;
+                const int col = w % NCOL, u = w / NCOL;
+                if (ITEMS0 % NT == 0 || w < ITEMS0) {
+                    Dft<R0, V>::run(x0[it]);
+#pragma unroll
+                    for (int q = 1; q < R0; ++q) {
+                        const float2 wq = tw_get<PL, 0>(tw, p.tw, (q - 1) * L0 + u);
+                        x0[it][q] = cmul(x0[it][q], wq.x, wq.y);
+                    }
+                    S *cb = buf + col * CS + u + (u >> 4);
+#pragma unroll
+                    for (int q = 0; q < R0; ++q) cb[q * L0 + ((q * L0) >> 4)] = E::pack(x0[it][q]);
+                }
             }
         }
         __syncthreads();
+        SPX_MARK(2)
 
         // ---- forward stages 1 .. NS-2: smem -> butterfly -> twiddle -> smem (in place)
-        if constexpr (NS > 2) { fwd_inner_pass<PL, MODE, NCOL, NT, 1>(buf, tw, tid); __syncthreads(); }
-        if constexpr (NS > 3) { fwd_inner_pass<PL, MODE, NCOL, NT, 2>(buf, tw, tid); __syncthreads(); }
+        // The exchange between stage NS-2 and the middle pass is a 16x16 transpose among the 16 threads that share
+        // (column, leading digits): with consecutive butterflies on consecutive lanes those threads are one half-warp,
+        // in this pass and in the middle pass alike, so __syncwarp() orders it and warps run on unsynchronised.
+        if constexpr (NS > 2) { fwd_inner_pass<PL, MODE, NCOL, NT, 1>(buf, tw, p.tw, tid); if constexpr (NS == 3 && kWarpLocal) __syncwarp(); else __syncthreads(); }
+        if constexpr (NS > 3) { fwd_inner_pass<PL, MODE, NCOL, NT, 2>(buf, tw, p.tw, tid); if constexpr (kWarpLocal) __syncwarp(); else __syncthreads(); }
 
+        SPX_MARK(3)
         // ---- middle pass: last forward butterfly -> gate (+memory) -> first inverse butterfly
         {
             constexpr int NBF = N / RL, ITEMS = NCOL * NBF;
@@ -503,22 +719,30 @@ __global__ void __launch_bounds__(NT, MINB) spectre_mix_kernel(const MixParams p
                 const int cabs = (ce0 + col) * CH;                 // first channel of this element
                 if constexpr (RFFT_ONLY) {
                     // half spectrum out (spectre.py:506 / :777): bins k <= n_fft/2 of this channel
-                    if ((ce0 + col) < CE) {
-                        float2 *sp = reinterpret_cast<float2 *>(p.out) + (long long)b * p.o_sb + cabs;
+                    float2 *sp = reinterpret_cast<float2 *>(p.out) + (long long)b * p.o_sb + cabs;
 #pragma unroll
-                        for (int q = 0; q < RL; ++q) {
-                            const int k = klow + PLAST * q;
-                            if (k <= N / 2) sp[(long long)k * p.o_sn] = E::pack(x[q]);
-                        }
+                    for (int q = 0; q < RL; ++q) {
+                        const int k = klow + PLAST * q;
+                        if (k <= N / 2) sp[(long long)k * p.o_sn] = make_float2(x[q].re, x[q].im);
                     }
                     continue;
                 }
                 const float2 *gs = gate_s + (cabs / p.group_width - g0) * GS;
+                // bins k = klow + PLAST q (q < RL/2) use G[k]; the mirrored half uses conj(G[N - k])
+                const int plo = klow + (klow >> 4);                // padded index of bin klow
+                const int nk = N - klow;                           // N - klow - PLAST q stays >= N/2 - ... >= 1
 #pragma unroll
                 for (int q = 0; q < RL; ++q) {
-                    const bool lower = q < RL / 2 || RL == 1;
-                    const int k = lower ? (klow + PLAST * q) : (N - klow - PLAST * q);  // table index (<= N/2)
-                    const float2 g = gs[k + (k >> 4)];
+                    const bool lower = q < RL / 2;
+                    int k, kp;
+                    if (lower) {
+                        k = klow + PLAST * q;
+                        kp = (PLAST % 16 == 0) ? plo + PLAST * q + ((PLAST * q) >> 4) : k + (k >> 4);
+                    } else {
+                        k = nk - PLAST * q;
+                        kp = k + (k >> 4);
+                    }
+                    const float2 g = gs[kp];
                     x[q] = lower ? cmul(x[q], g.x, g.y) : cmulc(x[q], g.x, g.y);
                     if (HAS_MEM) {
                         const float sgn = ((q == 0 || q == RL / 2) && klow == 0) ? 0.f : (lower ? p.inv_n : -p.inv_n);
@@ -531,41 +755,127 @@ __global__ void __launch_bounds__(NT, MINB) spectre_mix_kernel(const MixParams p
                 for (int m = 0; m < RL; ++m) cb[m] = E::pack(cswap(x[m]));
             }
         }
-        __syncthreads();
+        if constexpr (kWarpLocal && !RFFT_ONLY) __syncwarp(); else __syncthreads();
+        SPX_MARK(4)
         if constexpr (RFFT_ONLY) continue;
 
+        // the gate table is free again: start fetching the next tile's gate row, park it in registers
+        // across the inner inverse passes, and publish it before the last pass
+        float2 gnext[GK];
+        const int tile_next = tile + gridDim.x;
+        const bool fetch_next = gate_early && tile_next < p.num_tiles;
+        if (fetch_next) {
+            const int nb = tile_next / p.tiles_per_row;
+            const int ng = ((tile_next - nb * p.tiles_per_row) * NCOL * CH) / p.group_width;
+            gate_fetch<N, NT, GK>(gnext, p.gate + ((long long)nb * p.NG + ng) * (N / 2 + 1), tid);
+        }
+
         // ---- inverse stages NS-2 .. 1: smem -> twiddle -> butterfly -> smem (in place)
-        if constexpr (NS > 3) { inv_inner_pass<PL, MODE, NCOL, NT, 2>(buf, tw, tid); __syncthreads(); }
-        if constexpr (NS > 2) { inv_inner_pass<PL, MODE, NCOL, NT, 1>(buf, tw, tid); __syncthreads(); }
+        if constexpr (NS > 3) { inv_inner_pass<PL, MODE, NCOL, NT, 2>(buf, tw, p.tw, tid); __syncthreads(); }
+        if constexpr (NS > 2) { inv_inner_pass<PL, MODE, NCOL, NT, 1>(buf, tw, p.tw, tid); __syncthreads(); }
+        if (fetch_next) gate_put<N, NT, GK>(gate_s, gnext, tid, p.inv_n);
+        SPX_MARK(5)
 
         // ---- inverse stage 0: smem -> twiddle -> butterfly -> global
         {
-            constexpr int R = PL::R(0), L = PL::L(0);
-            constexpr int ITEMS = NCOL * L;
-            TOUT *ob = obase + (long long)b * p.o_sb + c0;
-            for (int w = tid; w < ITEMS; w += NT) {
+            Cx<V> x0[ITERS0][R0];
+#pragma unroll
+            for (int it = 0; it < ITERS0; ++it) {
+                const int w = tid + it * NT;
                 const int col = w % NCOL, u = w / NCOL;
-                const bool colok = (ce0 + col) < CE;
-                const S *cb = buf + col * CS + u + (u >> 4);
-                const float2 *tws = tw + PL::TWOFF(0) + u;
-                Cx<V> x[R];
+                if (ITEMS0 % NT == 0 || w < ITEMS0) {
+                    const S *cb = buf + col * CS + u + (u >> 4);
 #pragma unroll
-                for (int q = 0; q < R; ++q) {
-                    x[q] = cswap(E::unpack(cb[q * L + ((q * L) >> 4)]));
-                    if (q > 0) {
-                        const float2 wq = tws[(q - 1) * L];
-                        x[q] = cmul(x[q], wq.x, wq.y);
-                    }
+                    for (int q = 0; q < R0; ++q) x0[it][q] = cswap(E::unpack(cb[q * L0 + ((q * L0) >> 4)]));
                 }
-                Dft<R, V>::run(x);
+            }
+            if constexpr (TMA_IN) {
+                // the whole tile now lives in registers: hand the buffer to the TMA unit for the next tile
+                fence_proxy_async();
+                __syncthreads();
+                if (tid == 0) {
+                    const int nt = tile + gridDim.x;
+                    if (nt < p.num_tiles) issue_tile_load(nt);
+                }
+            }
+            TOUT *ob = obase + (long long)b * p.o_sb + c0;
 #pragma unroll
-                for (int m = 0; m < R; ++m) {
-                    const int row = u + m * L;
-                    if (colok && row < p.n_out) GIO<MODE, TOUT>::store(ob + (long long)row * p.o_sn + col * CH, cswap(x[m]));
+            for (int it = 0; it < ITERS0; ++it) {
+                const int w = tid + it * NT;
+                const int u = w / NCOL;
+                if (ITEMS0 % NT == 0 || w < ITEMS0) {
+#pragma unroll
+                    for (int q = 1; q < R0; ++q) {
+                        const float2 wq = tw_get<PL, 0>(tw, p.tw, (q - 1) * L0 + u);
+                        x0[it][q] = cmul(x0[it][q], wq.x, wq.y);
+                    }
+                    Dft<R0, V>::run(x0[it]);
+                }
+            }
+            SPX_MARK(6)
+            if constexpr (TMA_IN) {
+                // results leave through two shared staging buffers (STG_MB row blocks each) and TMA stores; a buffer is
+                // refilled only after the TMA unit has read it (mbarrier `free`), so stores of one round overlap the
+                // fill of the next and the landing of the next tile
+                using OT = typename Lin<MODE, TOUT>::T;
+                constexpr int MB = SM::STG_MB, NR = R0 / MB;
+                constexpr uint32_t OROWB = (uint32_t)(sizeof(OT) * NCOL);
+                constexpr uint32_t STGB = (uint32_t)SM::stg_bytes(OROWB);
+                static_assert(R0 % MB == 0, "row blocks per staging round must divide the stage-0 radix");
+#pragma unroll
+                for (int j = 0; j < NR; ++j) {
+                    const uint32_t kbuf = rnd & 1;
+                    if (rnd >= 2) mbar_wait(freeb + 8 * kbuf, ((rnd >> 1) - 1) & 1);
+                    OT *sb = reinterpret_cast<OT *>(stg + kbuf * STGB);
+#pragma unroll
+                    for (int it = 0; it < ITERS0; ++it) {
+                        const int w = tid + it * NT;
+                        const int col = w % NCOL, u = w / NCOL;
+                        if (ITEMS0 % NT == 0 || w < ITEMS0) {
+#pragma unroll
+                            for (int mm = 0; mm < MB; ++mm)
+                                sb[(mm * L0 + u) * NCOL + col] = Lin<MODE, TOUT>::put(cswap(x0[it][j * MB + mm]));
+                        }
+                    }
+                    fence_proxy_async();
+                    __syncthreads();
+                    if (tid == 0) {
+#pragma unroll
+                        for (int r0 = 0; r0 < SM::STG_ROWS; r0 += SM::OUT_BOX_ROWS)
+                            tma_store_3d(&tmap_out, smem_u32(sb) + r0 * OROWB, c0, j * SM::STG_ROWS + r0, b);
+                        tma_commit();
+                        tma_wait_read<1>();                       // every store but the one just issued has left smem
+                        if (rnd >= 1) mbar_arrive(freeb + 8 * (kbuf ^ 1));
+                    }
+                    ++rnd;
+                }
+            } else {
+#pragma unroll
+                for (int it = 0; it < ITERS0; ++it) {
+                    const int w = tid + it * NT;
+                    const int col = w % NCOL, u = w / NCOL;
+                    if (ITEMS0 % NT == 0 || w < ITEMS0) {
+                        TOUT *op = ob + (long long)u * p.o_sn + col * CH;
+                        if (full_tile) {
+#pragma unroll
+                            for (int m = 0; m < R0; ++m) GIO<MODE, TOUT>::store(op + (long long)(m * L0) * p.o_sn, cswap(x0[it][m]));
+                        } else {
+                            const bool colok = (ce0 + col) < CE;
+#pragma unroll
+                            for (int m = 0; m < R0; ++m)
+                                if (colok && u + m * L0 < p.n_out) GIO<MODE, TOUT>::store(op + (long long)(m * L0) * p.o_sn, cswap(x0[it][m]));
+                        }
+                    }
                 }
             }
         }
-        __syncthreads();  // the next tile's stage 0 overwrites the buffer and the gate tables
+        if constexpr (!TMA_IN) __syncthreads();  // the next tile's stage 0 overwrites the buffer and the gate tables
+        SPX_MARK(7)
+        ++tl_tile;
+    }
+#undef SPX_MARK
+    if constexpr (TMA_IN) {
+        if (tid == 0) tma_wait_all();   // staging buffers must outlive the last TMA stores
     }
 }
 

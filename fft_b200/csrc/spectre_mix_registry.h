@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stddef.h>
+#include <string.h>
 
 #include "spectre_mix_kernel.cuh"
 
@@ -16,9 +17,13 @@ struct KernelEntry {
     int threads;
     int minb;
     int twn;       // twiddle table entries
-    size_t (*smem_bytes)(int gate_tables);
-    cudaError_t (*launch)(const MixParams &p, int grid, bool has_mem, cudaStream_t st);
-    int (*occupancy)(int gate_tables, bool has_mem);
+    size_t (*smem_bytes)(int gate_tables, bool tma);
+    int out_box_rows;   // rows per TMA store box (TMA variant)
+    // tmap != nullptr selects the TMA-fed variant (only when tma_ok)
+    cudaError_t (*launch)(const MixParams &p, int grid, bool has_mem, const CUtensorMap *tmap_in, const CUtensorMap *tmap_out,
+                          cudaStream_t st);
+    int (*occupancy)(int gate_tables, bool has_mem, bool tma);
+    int tma_ok;    // 1: a TMA-fed variant exists (packed mode, landed row >= 16 bytes)
     // forward half only (half spectrum out); MODE_REAL variants only, else nullptr
     cudaError_t (*launch_rfft)(const MixParams &p, int grid, cudaStream_t st);
 };
@@ -26,34 +31,49 @@ struct KernelEntry {
 template <class PL, int MODE, int NCOL, int NT, int MINB, class TIO>
 struct Launcher {
     using SM = Smem<PL, MODE, NCOL>;
-    static size_t smem_bytes(int gate_tables) { return SM::bytes(gate_tables); }
-    template <bool HAS_MEM>
-    static const void *fn() {
-        return reinterpret_cast<const void *>(&spectre_mix_kernel<PL, MODE, NCOL, NT, MINB, TIO, TIO, HAS_MEM>);
+    static size_t smem_bytes(int gate_tables, bool tma) {
+        return SM::bytes(gate_tables, tma && kTma, sizeof(typename Lin<MODE, TIO>::T) * NCOL);
     }
-    static cudaError_t launch(const MixParams &p, int grid, bool has_mem, cudaStream_t st) {
-        const size_t sm = smem_bytes(p.gate_tables);
-        const void *f = has_mem ? fn<true>() : fn<false>();
+    // TMA delivers rows of NCOL elements; the box's inner extent must be a multiple of 16 bytes
+    static constexpr bool kTma = (MODE == MODE_QUAD) && ((sizeof(TIO) * 4 * NCOL) % 16 == 0);
+    template <bool HAS_MEM, bool TMA>
+    static const void *fn() {
+        return reinterpret_cast<const void *>(
+            &spectre_mix_kernel<PL, MODE, NCOL, NT, MINB, TIO, TIO, HAS_MEM, false, (TMA && kTma)>);
+    }
+    static const void *pick(bool has_mem, bool tma) {
+        if (tma && kTma) return has_mem ? fn<true, true>() : fn<false, true>();
+        return has_mem ? fn<true, false>() : fn<false, false>();
+    }
+    static cudaError_t launch(const MixParams &p, int grid, bool has_mem, const CUtensorMap *tmap, const CUtensorMap *tmap_out,
+                              cudaStream_t st) {
+        const size_t sm = smem_bytes(p.gate_tables, tmap != nullptr);
+        const void *f = pick(has_mem, tmap != nullptr);
         // opt in to > 48 KB dynamic shared memory (cheap; the driver caches the attribute per function)
         cudaError_t e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
         if (e != cudaSuccess) return e;
         MixParams pc = p;
-        void *args[] = {&pc};
+        alignas(64) CUtensorMap tm, tmo;
+        if (tmap) { tm = *tmap; tmo = *tmap_out; } else { memset(&tm, 0, sizeof(tm)); memset(&tmo, 0, sizeof(tmo)); }
+        void *args[] = {&pc, &tm, &tmo};
         return cudaLaunchKernel(f, dim3(grid), dim3(NT), args, sm, st);
     }
     static cudaError_t launch_rfft(const MixParams &p, int grid, cudaStream_t st) {
         static_assert(MODE == MODE_REAL, "rfft-only is built for MODE_REAL");
-        const size_t sm = smem_bytes(0);
+        const size_t sm = smem_bytes(0, false);
         const void *f = reinterpret_cast<const void *>(&spectre_mix_kernel<PL, MODE, NCOL, NT, MINB, TIO, TIO, false, true>);
         cudaError_t e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
         if (e != cudaSuccess) return e;
         MixParams pc = p;
-        void *args[] = {&pc};
+        alignas(64) CUtensorMap tm, tmo;
+        memset(&tm, 0, sizeof(tm));
+        memset(&tmo, 0, sizeof(tmo));
+        void *args[] = {&pc, &tm, &tmo};
         return cudaLaunchKernel(f, dim3(grid), dim3(NT), args, sm, st);
     }
-    static int occupancy(int gate_tables, bool has_mem) {
-        const size_t sm = smem_bytes(gate_tables);
-        const void *f = has_mem ? fn<true>() : fn<false>();
+    static int occupancy(int gate_tables, bool has_mem, bool tma) {
+        const size_t sm = smem_bytes(gate_tables, tma);
+        const void *f = pick(has_mem, tma);
         if (cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm) != cudaSuccess) {
             cudaGetLastError();
             return 0;
@@ -83,8 +103,10 @@ struct RfftPtr<PL, MODE_REAL, NCOL, NT, MINB, TIO> {
         (R0) * (R1) * (R2) * (R3), {R0, R1, R2, R3}, MODE, IOCODE, NCOL, NT, MINB,                            \
             ::spx::Plan<R0, R1, R2, R3>::TWN,                                                                 \
             &::spx::Launcher<::spx::Plan<R0, R1, R2, R3>, MODE, NCOL, NT, MINB, TIO>::smem_bytes,             \
+            ::spx::Smem<::spx::Plan<R0, R1, R2, R3>, MODE, NCOL>::OUT_BOX_ROWS,                               \
             &::spx::Launcher<::spx::Plan<R0, R1, R2, R3>, MODE, NCOL, NT, MINB, TIO>::launch,                 \
             &::spx::Launcher<::spx::Plan<R0, R1, R2, R3>, MODE, NCOL, NT, MINB, TIO>::occupancy,              \
+            ::spx::Launcher<::spx::Plan<R0, R1, R2, R3>, MODE, NCOL, NT, MINB, TIO>::kTma ? 1 : 0,            \
             ::spx::RfftPtr<::spx::Plan<R0, R1, R2, R3>, MODE, NCOL, NT, MINB, TIO>::get()                     \
     }
 

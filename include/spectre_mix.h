@@ -101,6 +101,12 @@ int spectre_mix_set_tile_channels(int tile_channels);
 /* Enable (default) / disable the L2 prefetch of a CTA's next tile.  For experiments only. */
 int spectre_mix_set_prefetch(int enable);
 
+/* Enable (default) / disable TMA-staged tile loads (falls back to direct 128-bit global loads).  For experiments only. */
+int spectre_mix_set_tma(int enable);
+
+/* Debug: device buffer of grid * 8 tiles * 8 uint64 that receives per-phase %globaltimer stamps (NULL = off). */
+int spectre_mix_set_timeline(void *device_buffer);
+
 #ifdef __cplusplus
 }
 #endif

@@ -193,6 +193,28 @@ def test_dc_nyquist_imag_ignored(fb, dev):
     assert torch.equal(y0, y1)
 
 
+def test_tma_and_direct_load_paths_agree(fb, oracle, dev):
+    """The TMA-staged tile load and the direct 128-bit global load feed the same arithmetic: bitwise equal."""
+    from fft_b200 import _lib
+    lib = _lib.load()
+    for (B, N, n_fft, C, dg) in [(3, 4096, 4096, 64, 16), (2, 900, 1024, 40, 8), (2, 2048, 2048, 32, 16)]:
+        V, gate, mem = _rand_case(B, N, n_fft, C, dg, True, seed=21 + N)
+        args = (V.to(dev), gate.to(dev), mem.to(dev))
+        try:
+            lib.spectre_mix_set_tma(0)
+            y0 = fb.spectral_mix(*args, n_fft=n_fft, group_width=dg)
+            lib.spectre_mix_set_tma(1)
+            lib.spectre_mix_set_prefetch(0)
+            y1 = fb.spectral_mix(*args, n_fft=n_fft, group_width=dg)
+            lib.spectre_mix_set_prefetch(1)
+            y2 = fb.spectral_mix(*args, n_fft=n_fft, group_width=dg)
+        finally:
+            lib.spectre_mix_set_tma(1)
+            lib.spectre_mix_set_prefetch(1)
+        assert torch.equal(y0, y1) and torch.equal(y1, y2)
+        _check(y1, oracle.mix_flat(V, gate, n_fft, dg, mem).numpy())
+
+
 # --------------------------------------------------------------------------- layouts
 def test_strided_views(fb, oracle, dev):
     """V as a channel slice of a wider tensor, memory as a chunk view (row stride > C), as spectre.py:703-707 makes them."""

@@ -15,11 +15,12 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from fft_b200 import _lib  # noqa: E402
 
 
-def time_case(lib, n_fft, C, dg, B, tile, prefetch, dtype=torch.float32, mem=False, reps=10, N=None):
+def time_case(lib, n_fft, C, dg, B, tile, prefetch, dtype=torch.float32, mem=False, reps=10, N=None, tma=1):
     dev = torch.device("cuda")
     N = N or n_fft
     lib.spectre_mix_set_tile_channels(tile)
     lib.spectre_mix_set_prefetch(prefetch)
+    lib.spectre_mix_set_tma(tma)
     gen = torch.Generator(device=dev).manual_seed(0)
     sets = 2
     V = [torch.randn(B, N, C, device=dev, generator=gen).to(dtype) for _ in range(sets)]
@@ -65,9 +66,9 @@ def main():
     C, dg = 768, 16
     cases = [
         # n_fft, B, tiles to try
-        (4096, 64, [0, 8, 4]),
-        (1024, 256, [0, 8, 16]),
-        (2048, 128, [0, 8, 4]),
+        (4096, 64, [0]),
+        (1024, 256, [8, 16]),
+        (2048, 128, [0]),
         (8192, 32, [0]),
         (16384, 16, [0]),
         (512, 512, [0]),
@@ -76,9 +77,9 @@ def main():
     ]
     for n_fft, B, tiles in cases:
         for tile in tiles:
-            for pf in (1, 0):
-                r = time_case(lib, n_fft, C, dg, B, tile, pf)
-                r.update(n_fft=n_fft, B=B, tile=tile, prefetch=pf, dtype="f32")
+            for tma, pf in ((1, 1), (1, 0), (0, 0)):
+                r = time_case(lib, n_fft, C, dg, B, tile, pf, tma=tma)
+                r.update(n_fft=n_fft, B=B, tile=tile, prefetch=pf, tma=tma, dtype="f32")
                 print(json.dumps(r), flush=True)
                 res.append(r)
     for n_fft, B in [(4096, 64), (1024, 256)]:
@@ -96,6 +97,7 @@ def main():
     res.append(r)
     lib.spectre_mix_set_tile_channels(0)
     lib.spectre_mix_set_prefetch(1)
+    lib.spectre_mix_set_tma(1)
     os.makedirs(os.path.dirname(args.out) or ".", exist_ok=True)
     json.dump(res, open(args.out, "w"), indent=1)
 
