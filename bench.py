@@ -243,12 +243,9 @@ def main():
         ev1.record(stream)
         barrier()
     elapsed_ms = ev0.elapsed_time(ev1)
-    checksum = outs[0].double().sum()
-    t = torch.tensor([elapsed_ms], device=dev, dtype=torch.float64)
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dist.all_reduce(checksum, op=dist.ReduceOp.SUM)
-    elapsed_ms = float(t.item())
+    from fft_b200.dist import reduce_measurement
+    # whole-job view: max time over ranks, total tokens, summed output checksum (no data-path collective exists)
+    elapsed_ms, _, checksum = reduce_measurement(elapsed_ms, B * SEQ * args.steps, float(outs[0].double().sum()), device=dev)
     tokens_per_step = B * SEQ * world
     value = tokens_per_step * args.steps / (elapsed_ms * 1e-3)
     ms_per_step = elapsed_ms / args.steps
@@ -305,7 +302,7 @@ def main():
                        "l2": f"inputs larger than L2: {B * SEQ * D_MODEL * 4 / 1e6:.0f} MB per tensor, {nsets} buffer sets alternated",
                        "plan": fft_b200.plan_info(B, SEQ, SEQ, D_MODEL, D_G)},
             "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu, "clocks": clk.summary(),
-            "gpu_launches": args.steps * world, "checksum": float(checksum.item()),
+            "gpu_launches": args.steps * world, "checksum": checksum,
         }
         print(json.dumps(line), flush=True)
     if dist is not None:
