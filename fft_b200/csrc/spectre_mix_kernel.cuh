@@ -505,6 +505,19 @@ struct Lin {  // PAIR / REAL never use the TMA path
 };
 
 constexpr int kTmaBoxRows = 256;
+// The TMA variant adds one producer warpgroup (one elected lane works).  A whole warpgroup, because setmaxnreg moves
+// registers between warpgroups: the producer shrinks to 24 registers and the compute warps take what it frees.
+constexpr int kProducerThreads = 128;
+// CTAs with fewer compute threads keep the producer duties on compute thread 0 (an extra warpgroup would cost them
+// occupancy and registers)
+constexpr int kSepProducerMinThreads = 256;
+__host__ __device__ constexpr int reg_floor8(int r) { return r / 8 * 8; }
+// register budget of the compute warps after the hand-over (launch allocation = nominal * all threads)
+__host__ __device__ constexpr int compute_regs(int nt, int minb) {
+    return reg_floor8((reg_floor8(65536 / (minb * (nt + kProducerThreads))) * (nt + kProducerThreads) - 24 * kProducerThreads) / nt) > 128
+               ? 128
+               : reg_floor8((reg_floor8(65536 / (minb * (nt + kProducerThreads))) * (nt + kProducerThreads) - 24 * kProducerThreads) / nt);
+}
 
 // gate row -> registers (all loads in flight), registers -> padded shared table
 template <int N, int NT, int GK>
@@ -527,6 +540,13 @@ __device__ __forceinline__ void gate_put(float2 *gs, const float2 (&gv)[GK], int
     }
 }
 
+// barrier over the NT compute threads only (the TMA producer warp of the TMA variant never joins it)
+template <int NT, bool NAMED>
+__device__ __forceinline__ void cta_sync() {
+    if constexpr (NAMED) asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory");
+    else __syncthreads();
+}
+
 // ------------------------------------------------------------------ the kernel
 // One persistent CTA per resident slot; each loop iteration transforms one tile = all n_fft rows of NCOL
 // elements (CH channels each) of one batch row.  RFFT_ONLY: stop after the forward half and write the half
@@ -534,7 +554,7 @@ __device__ __forceinline__ void gate_put(float2 *gs, const float2 (&gv)[GK], int
 // tile is prefetched into L2 by the TMA unit; otherwise stage 0 loads straight from global into registers.
 template <class PL, int MODE, int NCOL, int NT, int MINB, class TIN, class TOUT, bool HAS_MEM, bool RFFT_ONLY = false,
           bool TMA_IN = false>
-__global__ void __launch_bounds__(NT, MINB)
+__global__ void __launch_bounds__(NT + ((TMA_IN && NT >= kSepProducerMinThreads) ? kProducerThreads : 0), MINB)
     spectre_mix_kernel(const MixParams p, const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_out) {
     using E = Elem<MODE>;
     using V = typename E::V;
@@ -557,12 +577,14 @@ __global__ void __launch_bounds__(NT, MINB)
     float2 *tw = reinterpret_cast<float2 *>(smem_raw + SM::data_bytes);
     float2 *gate_s = reinterpret_cast<float2 *>(smem_raw + SM::data_bytes + SM::tw_bytes);
     constexpr int GS = (int)(SM::gate_bytes_one / sizeof(float2));
-    // mbarriers (tile landed, staging buffer 0/1 free) and the output staging buffers live after the gate tables
+    // mbarriers and the output staging buffers live after the gate tables
+    //   +0 landed (TMA tx)   +8 buffer free (NW warps)   +16/+24 staging full (NW warps)   +32/+40 staging free (producer)
     const size_t bar_off = ((SM::base_bytes(p.gate_tables) + 127) / 128) * 128;
     const uint32_t bar = smem_u32(smem_raw + bar_off);
-    const uint32_t freeb = bar + 16;
+    const uint32_t bar_buf_free = bar + 8, bar_stg_full = bar + 16, bar_stg_free = bar + 32;
     unsigned char *stg = smem_raw + bar_off + SM::bar_bytes;
-
+    constexpr int NW = NT / 32;
+    constexpr bool SEP = TMA_IN && (NT >= kSepProducerMinThreads);   // separate producer warpgroup
     const int tid = threadIdx.x;
     for (int i = tid; i < TwPolicy<PL>::SMEM_N; i += NT) tw[i] = p.tw[PL::TWOFF(TwPolicy<PL>::FROM) + i];
     // first __syncthreads of the tile loop publishes the table
@@ -589,14 +611,62 @@ __global__ void __launch_bounds__(NT, MINB)
 #pragma unroll 1
         for (int r0 = 0; r0 < p.n_in; r0 += BOXR) tma_prefetch_3d(&tmap, tc, r0, tb);
     };
+    using OTs = typename Lin<MODE, TOUT>::T;
+    constexpr uint32_t OROWB = (uint32_t)(sizeof(OTs) * NCOL);
+    constexpr uint32_t STGB = (uint32_t)SM::stg_bytes(OROWB);
+    constexpr int NR = PL::R(0) / SM::STG_MB;                          // output staging rounds per tile
+    // producer duties (one thread): next-tile load once the buffer is free; TMA stores of a filled staging buffer
+    uint32_t rnd_p = 0;
+    auto producer_next_load = [&](int tile, int it) {
+        const int nt = tile + gridDim.x;
+        mbar_wait(bar_buf_free, it & 1);       // every compute warp has pulled `tile` out of the buffer
+        if (nt < p.num_tiles) issue_tile_load(nt);
+    };
+    auto producer_store_round = [&](int tile, int j) {
+        const int tb = tile / p.tiles_per_row;
+        const int tc = (tile - tb * p.tiles_per_row) * NCOL * CH;
+        const uint32_t kbuf = rnd_p & 1;
+        mbar_wait(bar_stg_full + 8 * kbuf, (rnd_p >> 1) & 1);
+        const uint32_t sb = smem_u32(stg + kbuf * STGB);
+#pragma unroll 1
+        for (int r0 = 0; r0 < SM::STG_ROWS; r0 += SM::OUT_BOX_ROWS)
+            tma_store_3d(&tmap_out, sb + r0 * OROWB, tc, j * SM::STG_ROWS + r0, tb);
+        tma_commit();
+        tma_wait_read<1>();                    // every store but the one just issued has left shared memory
+        if (rnd_p >= 1) mbar_arrive(bar_stg_free + 8 * (kbuf ^ 1));
+        ++rnd_p;
+    };
     if constexpr (TMA_IN) {
-        if (tid == 0) {
+        if (tid == (SEP ? NT : 0)) {
             mbar_init(bar, 1);
-            mbar_init(freeb, 1);
-            mbar_init(freeb + 8, 1);
+            mbar_init(bar_buf_free, NW);
+            mbar_init(bar_stg_full, NW);
+            mbar_init(bar_stg_full + 8, NW);
+            mbar_init(bar_stg_free, 1);
+            mbar_init(bar_stg_free + 8, 1);
             if ((int)blockIdx.x < p.num_tiles) issue_tile_load(blockIdx.x);
         }
+        __syncthreads();   // all threads, once: barriers are initialised
+        if constexpr (SEP) {
+            if (tid >= NT) {
+                asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
+                // ---------------- TMA producer warpgroup: every bulk-tensor load / store of this CTA is issued here, so
+                // no compute warp ever waits for the TMA queue.  One elected lane does the work.
+                if (tid == NT) {
+                    int it = 0;
+                    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+                        producer_next_load(tile, it);
+                        for (int j = 0; j < NR; ++j) producer_store_round(tile, j);
+                        if (p.prefetch && tile + 2 * (int)gridDim.x < p.num_tiles) prefetch_tile(tile + 2 * gridDim.x);
+                    }
+                    tma_wait_all();   // staging buffers must outlive the last TMA stores
+                }
+                return;
+            }
+            asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(compute_regs(NT, MINB)));
+        }
     }
+    int tile_it = 0;
     uint32_t parity = 0;
     int tl_tile = 0;
 #define SPX_MARK(slot)                                                                                   \
@@ -634,8 +704,6 @@ __global__ void __launch_bounds__(NT, MINB)
                 mbar_wait(bar, parity);
                 parity ^= 1;
                 SPX_MARK(1)
-                // this tile is on chip: let the TMA unit pull the next one into L2 while we transform
-                if (p.prefetch && tid == 0 && tile + (int)gridDim.x < p.num_tiles) prefetch_tile(tile + gridDim.x);
                 const LT *lin = reinterpret_cast<const LT *>(smem_raw);
 #pragma unroll
                 for (int it = 0; it < ITERS0; ++it) {
@@ -646,7 +714,7 @@ __global__ void __launch_bounds__(NT, MINB)
                         for (int m = 0; m < R0; ++m) x0[it][m] = Lin<MODE, TIN>::get(lin[(u + m * L0) * NCOL + col]);
                     }
                 }
-                __syncthreads();   // every landed element is in registers: the buffer may be rewritten in place
+                cta_sync<NT, SEP>();   // every landed element is in registers: the buffer may be rewritten in place
             } else {
                 const TIN *vb = vbase + (long long)b * p.v_sb + c0;
 #pragma unroll
@@ -692,15 +760,15 @@ __global__ void __launch_bounds__(NT, MINB)
                 }
             }
         }
-        __syncthreads();
+        cta_sync<NT, SEP>();
         SPX_MARK(2)
 
         // ---- forward stages 1 .. NS-2: smem -> butterfly -> twiddle -> smem (in place)
         // The exchange between stage NS-2 and the middle pass is a 16x16 transpose among the 16 threads that share
         // (column, leading digits): with consecutive butterflies on consecutive lanes those threads are one half-warp,
         // in this pass and in the middle pass alike, so __syncwarp() orders it and warps run on unsynchronised.
-        if constexpr (NS > 2) { fwd_inner_pass<PL, MODE, NCOL, NT, 1>(buf, tw, p.tw, tid); if constexpr (NS == 3 && kWarpLocal) __syncwarp(); else __syncthreads(); }
-        if constexpr (NS > 3) { fwd_inner_pass<PL, MODE, NCOL, NT, 2>(buf, tw, p.tw, tid); if constexpr (kWarpLocal) __syncwarp(); else __syncthreads(); }
+        if constexpr (NS > 2) { fwd_inner_pass<PL, MODE, NCOL, NT, 1>(buf, tw, p.tw, tid); if constexpr (NS == 3 && kWarpLocal) __syncwarp(); else cta_sync<NT, SEP>(); }
+        if constexpr (NS > 3) { fwd_inner_pass<PL, MODE, NCOL, NT, 2>(buf, tw, p.tw, tid); if constexpr (kWarpLocal) __syncwarp(); else cta_sync<NT, SEP>(); }
 
         SPX_MARK(3)
         // ---- middle pass: last forward butterfly -> gate (+memory) -> first inverse butterfly
@@ -755,7 +823,7 @@ __global__ void __launch_bounds__(NT, MINB)
                 for (int m = 0; m < RL; ++m) cb[m] = E::pack(cswap(x[m]));
             }
         }
-        if constexpr (kWarpLocal && !RFFT_ONLY) __syncwarp(); else __syncthreads();
+        if constexpr (kWarpLocal && !RFFT_ONLY) __syncwarp(); else cta_sync<NT, SEP>();
         SPX_MARK(4)
         if constexpr (RFFT_ONLY) continue;
 
@@ -771,8 +839,8 @@ __global__ void __launch_bounds__(NT, MINB)
         }
 
         // ---- inverse stages NS-2 .. 1: smem -> twiddle -> butterfly -> smem (in place)
-        if constexpr (NS > 3) { inv_inner_pass<PL, MODE, NCOL, NT, 2>(buf, tw, p.tw, tid); __syncthreads(); }
-        if constexpr (NS > 2) { inv_inner_pass<PL, MODE, NCOL, NT, 1>(buf, tw, p.tw, tid); __syncthreads(); }
+        if constexpr (NS > 3) { inv_inner_pass<PL, MODE, NCOL, NT, 2>(buf, tw, p.tw, tid); cta_sync<NT, SEP>(); }
+        if constexpr (NS > 2) { inv_inner_pass<PL, MODE, NCOL, NT, 1>(buf, tw, p.tw, tid); cta_sync<NT, SEP>(); }
         if (fetch_next) gate_put<N, NT, GK>(gate_s, gnext, tid, p.inv_n);
         SPX_MARK(5)
 
@@ -790,12 +858,13 @@ __global__ void __launch_bounds__(NT, MINB)
                 }
             }
             if constexpr (TMA_IN) {
-                // the whole tile now lives in registers: hand the buffer to the TMA unit for the next tile
+                // this warp's share of the tile now lives in registers; when all warps have said so the producer
+                // hands the buffer to the TMA unit for the next tile
                 fence_proxy_async();
-                __syncthreads();
-                if (tid == 0) {
-                    const int nt = tile + gridDim.x;
-                    if (nt < p.num_tiles) issue_tile_load(nt);
+                __syncwarp();
+                if ((tid & 31) == 0) mbar_arrive(bar_buf_free);
+                if constexpr (!SEP) {
+                    if (tid == 0) producer_next_load(tile, tile_it);
                 }
             }
             TOUT *ob = obase + (long long)b * p.o_sb + c0;
@@ -818,14 +887,12 @@ __global__ void __launch_bounds__(NT, MINB)
                 // refilled only after the TMA unit has read it (mbarrier `free`), so stores of one round overlap the
                 // fill of the next and the landing of the next tile
                 using OT = typename Lin<MODE, TOUT>::T;
-                constexpr int MB = SM::STG_MB, NR = R0 / MB;
-                constexpr uint32_t OROWB = (uint32_t)(sizeof(OT) * NCOL);
-                constexpr uint32_t STGB = (uint32_t)SM::stg_bytes(OROWB);
+                constexpr int MB = SM::STG_MB;
                 static_assert(R0 % MB == 0, "row blocks per staging round must divide the stage-0 radix");
 #pragma unroll
                 for (int j = 0; j < NR; ++j) {
                     const uint32_t kbuf = rnd & 1;
-                    if (rnd >= 2) mbar_wait(freeb + 8 * kbuf, ((rnd >> 1) - 1) & 1);
+                    if (rnd >= 2) mbar_wait(bar_stg_free + 8 * kbuf, ((rnd >> 1) - 1) & 1);
                     OT *sb = reinterpret_cast<OT *>(stg + kbuf * STGB);
 #pragma unroll
                     for (int it = 0; it < ITERS0; ++it) {
@@ -838,14 +905,10 @@ __global__ void __launch_bounds__(NT, MINB)
                         }
                     }
                     fence_proxy_async();
-                    __syncthreads();
-                    if (tid == 0) {
-#pragma unroll
-                        for (int r0 = 0; r0 < SM::STG_ROWS; r0 += SM::OUT_BOX_ROWS)
-                            tma_store_3d(&tmap_out, smem_u32(sb) + r0 * OROWB, c0, j * SM::STG_ROWS + r0, b);
-                        tma_commit();
-                        tma_wait_read<1>();                       // every store but the one just issued has left smem
-                        if (rnd >= 1) mbar_arrive(freeb + 8 * (kbuf ^ 1));
+                    __syncwarp();
+                    if ((tid & 31) == 0) mbar_arrive(bar_stg_full + 8 * kbuf);
+                    if constexpr (!SEP) {
+                        if (tid == 0) producer_store_round(tile, j);
                     }
                     ++rnd;
                 }
@@ -869,12 +932,13 @@ __global__ void __launch_bounds__(NT, MINB)
                 }
             }
         }
-        if constexpr (!TMA_IN) __syncthreads();  // the next tile's stage 0 overwrites the buffer and the gate tables
+        if constexpr (!TMA_IN) cta_sync<NT, SEP>();  // the next tile's stage 0 overwrites the buffer and the gate tables
         SPX_MARK(7)
         ++tl_tile;
+        ++tile_it;
     }
 #undef SPX_MARK
-    if constexpr (TMA_IN) {
+    if constexpr (TMA_IN && !SEP) {
         if (tid == 0) tma_wait_all();   // staging buffers must outlive the last TMA stores
     }
 }

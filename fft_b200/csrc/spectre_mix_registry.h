@@ -56,7 +56,7 @@ struct Launcher {
         alignas(64) CUtensorMap tm, tmo;
         if (tmap) { tm = *tmap; tmo = *tmap_out; } else { memset(&tm, 0, sizeof(tm)); memset(&tmo, 0, sizeof(tmo)); }
         void *args[] = {&pc, &tm, &tmo};
-        return cudaLaunchKernel(f, dim3(grid), dim3(NT), args, sm, st);
+        return cudaLaunchKernel(f, dim3(grid), dim3(NT + ((tmap != nullptr && kTma && NT >= kSepProducerMinThreads) ? kProducerThreads : 0)), args, sm, st);
     }
     static cudaError_t launch_rfft(const MixParams &p, int grid, cudaStream_t st) {
         static_assert(MODE == MODE_REAL, "rfft-only is built for MODE_REAL");
@@ -79,7 +79,7 @@ struct Launcher {
             return 0;
         }
         int nb = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, f, NT, sm) != cudaSuccess) {
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, f, NT + ((tma && kTma && NT >= kSepProducerMinThreads) ? kProducerThreads : 0), sm) != cudaSuccess) {
             cudaGetLastError();
             return 0;
         }

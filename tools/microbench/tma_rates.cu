@@ -100,8 +100,9 @@ int main() {
     unsigned long long *ns;
     CK(cudaMalloc(&ns, 148 * 8));
     int sms = 148;
+    if (getenv("TMA_SMS")) sms = atoi(getenv("TMA_SMS"));
     for (int wbytes : {32, 64, 128}) {
-        for (int boxr : {256, 64, 16}) {
+        for (int boxr : {256, 64}) {
             const int rows = 128 * 1024 / wbytes / ((wbytes == 32) ? 1 : 1);  // 128 KB tiles
             const int trows = rows > N ? N : rows;
             if (trows < boxr) continue;
