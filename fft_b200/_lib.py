@@ -27,6 +27,8 @@ SYMBOLS = (
     "spectre_mix_set_prefetch",
     "spectre_mix_set_tma",
     "spectre_mix_set_timeline",
+    "spectre_mix_set_tmem",
+    "spectre_mix_set_skew_ns",
 )
 
 
@@ -82,6 +84,10 @@ def load():
         lib.spectre_mix_set_prefetch.argtypes = [i32]
         lib.spectre_mix_set_tma.restype = i32
         lib.spectre_mix_set_tma.argtypes = [i32]
+        lib.spectre_mix_set_skew_ns.restype = i32
+        lib.spectre_mix_set_skew_ns.argtypes = [i32]
+        lib.spectre_mix_set_tmem.restype = i32
+        lib.spectre_mix_set_tmem.argtypes = [i32]
         lib.spectre_mix_set_timeline.restype = i32
         lib.spectre_mix_set_timeline.argtypes = [vp]
         _lib = lib

@@ -41,8 +41,10 @@ int cuda_fail(cudaError_t e, const char *what) {
 }
 
 int g_tile_channels_override = 0;
-int g_prefetch = 0;   // L2 prefetch of the next tile: measured neutral-to-harmful so far (profiles/), off by default
+int g_prefetch = 1;   // L2 prefetch of the tile after next by the TMA unit (helps the TMEM-staged variant, neutral elsewhere)
 int g_use_tma = 1;
+int g_use_tmem = 1;
+int g_skew_ns = 0;
 unsigned long long *g_timeline = nullptr;
 
 // ---------------------------------------------------------------- kernel registry
@@ -177,7 +179,7 @@ int choose(const DeviceState &st, int n_fft, int dtype, int mode_max, int C, int
             else if (tw % group_width == 0) gt = tw / group_width;
             else gt = (tw + group_width - 1) / group_width + 1;
             if (no_gate) gt = 0;
-            const size_t sm = k.smem_bytes(gt, false);
+            const size_t sm = k.smem_bytes(gt, false, false);
             if ((int)sm > st.max_smem_optin) continue;
             const int ce = C / ch;
             Choice c;
@@ -210,11 +212,11 @@ int check_common(int B, int N, int n_fft, int C, int group_width) {
     return 0;
 }
 
-int occupancy_of(DeviceState &st, const Choice &c, bool has_mem, bool tma) {
-    auto key = std::make_pair(c.k, c.gate_tables * 4 + (has_mem ? 1 : 0) + (tma ? 2 : 0));
+int occupancy_of(DeviceState &st, const Choice &c, bool has_mem, bool tma, bool tmem = false) {
+    auto key = std::make_pair(c.k, c.gate_tables * 8 + (has_mem ? 1 : 0) + (tma ? 2 : 0) + (tmem ? 4 : 0));
     auto it = st.occupancy.find(key);
     if (it != st.occupancy.end()) return it->second;
-    int occ = c.k->occupancy(c.gate_tables, has_mem, tma);
+    int occ = c.k->occupancy(c.gate_tables, has_mem, tma, tmem);
     st.occupancy[key] = occ;
     return occ;
 }
@@ -282,6 +284,16 @@ int spectre_mix_set_timeline(void *device_buffer) {
     return 0;
 }
 
+int spectre_mix_set_skew_ns(int ns) {
+    g_skew_ns = ns < 0 ? 0 : ns;
+    return 0;
+}
+
+int spectre_mix_set_tmem(int enable) {
+    g_use_tmem = enable ? 1 : 0;
+    return 0;
+}
+
 int spectre_mix_set_tma(int enable) {
     g_use_tma = enable ? 1 : 0;
     return 0;
@@ -336,18 +348,20 @@ int spectre_mix_fwd(const void *v, int v_dtype, int64_t v_stride_b, int64_t v_st
     p.inv_n = 1.0f / (float)n_fft;
     p.prefetch = g_prefetch;
     p.timeline = g_timeline;
+    p.skew_ns = g_skew_ns;
 
     // TMA-fed variant when V's layout can be described to the TMA unit; otherwise direct 128-bit global loads
     alignas(64) CUtensorMap tmap, tmap_out;
     const int tile_ch = mode_channels(c.k->mode) * c.k->ncol;
-    bool tma = g_use_tma && c.k->tma_ok && (int)c.k->smem_bytes(c.gate_tables, true) <= st->max_smem_optin &&
+    bool tma = g_use_tma && c.k->tma_ok && (int)c.k->smem_bytes(c.gate_tables, true, false) <= st->max_smem_optin &&
                tma_layout_ok(v, v_dtype, v_stride_b, v_stride_n) && tma_layout_ok(out, out_dtype, out_stride_b, out_stride_n) &&
                make_v_tensor_map(&tmap, v, v_dtype, v_stride_b, v_stride_n, B, n_io, C, std::min(n_fft, spx::kTmaBoxRows),
                                  tile_ch) &&
                make_v_tensor_map(&tmap_out, out, out_dtype, out_stride_b, out_stride_n, B, n_io, C, c.k->out_box_rows, tile_ch);
-    const int occ = std::max(1, occupancy_of(*st, c, mem != nullptr, tma));
+    const bool tmem = tma && g_use_tmem && c.k->tmem_ok && (int)c.k->smem_bytes(c.gate_tables, true, true) <= st->max_smem_optin;
+    const int occ = std::max(1, occupancy_of(*st, c, mem != nullptr, tma, tmem));
     const int grid = std::min(p.num_tiles, st->sm_count * occ);
-    cudaError_t e = c.k->launch(p, grid, mem != nullptr, tma ? &tmap : nullptr, tma ? &tmap_out : nullptr,
+    cudaError_t e = c.k->launch(p, grid, mem != nullptr, tma ? &tmap : nullptr, tma ? &tmap_out : nullptr, tmem,
                                 reinterpret_cast<cudaStream_t>(stream));
     if (e != cudaSuccess) return cuda_fail(e, "kernel launch");
     return 0;
@@ -370,7 +384,7 @@ int spectre_mix_plan(int v_dtype, int out_dtype, int has_mem, int B, int N, int 
     info->tile_channels = mode_channels(c.k->mode) * c.k->ncol;
     info->threads = c.k->threads;
     info->ctas_per_sm = std::max(1, occupancy_of(*st, c, has_mem != 0, g_use_tma && c.k->tma_ok));
-    info->smem_bytes = (int)c.k->smem_bytes(c.gate_tables, g_use_tma && c.k->tma_ok);
+    info->smem_bytes = (int)c.k->smem_bytes(c.gate_tables, g_use_tma && c.k->tma_ok, g_use_tma && g_use_tmem && c.k->tmem_ok);
     info->grid = std::min(B * c.tiles_per_row, st->sm_count * info->ctas_per_sm);
     info->launches = 1;
     info->algorithmic_bytes = algorithmic_bytes(v_dtype, has_mem != 0, B, N, n_fft, C, group_width);

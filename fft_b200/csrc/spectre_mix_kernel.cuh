@@ -51,6 +51,7 @@ struct MixParams {
     int gate_tables;      // gate groups a tile may touch (smem sized for this many)
     float inv_n;
     int prefetch;         // 1: prefetch the CTA's next tile into L2 while this one is transformed
+    int skew_ns;          // experiment: delay half of the warps by this much before the warp-local passes
     unsigned long long *timeline;  // optional: per-CTA phase timestamps (ns) for tools/timeline.py, else nullptr
 };
 
@@ -202,6 +203,9 @@ struct Plan {
 };
 
 __host__ __device__ constexpr int cmax(int a, int b) { return a > b ? a : b; }
+// ring of TMA boxes shared by both directions of the TMEM variant: while a tile is parked all but one slot hold
+// loads in flight (latency cover), while results are drained all of them are store sources
+constexpr int kTmemSlots = 5;
 
 // Which stages keep their twiddles in shared memory: all of them while the tables fit beside the tile; from
 // n_fft = 8192 the (largest) stage-0 table is read through L2 instead, at 16384 every table is.
@@ -329,8 +333,10 @@ struct Smem {
     __host__ __device__ static constexpr size_t stg_bytes(size_t row_bytes) { return (size_t)STG_ROWS * row_bytes; }
     static constexpr size_t bar_bytes = 128;
     __host__ __device__ static constexpr size_t base_bytes(int gate_tables) { return data_bytes + tw_bytes + gate_bytes_one * (size_t)gate_tables; }
-    static constexpr size_t bytes(int gate_tables, bool tma = false, size_t row_bytes = 0) {
-        return ((base_bytes(gate_tables) + 127) / 128) * 128 + bar_bytes + (tma ? 2 * stg_bytes(row_bytes) : 0);
+    // TMEM variant: ring of kTmemSlots + kTmemStoreSlots TMA boxes (256 rows each) instead of the staging buffers
+    static constexpr size_t bytes(int gate_tables, bool tma = false, size_t row_bytes = 0, bool tmem = false) {
+        return ((base_bytes(gate_tables) + 127) / 128) * 128 + bar_bytes +
+               (tmem ? (size_t)kTmemSlots * 256 * row_bytes : (tma ? 2 * stg_bytes(row_bytes) : 0));
     }
 };
 
@@ -473,6 +479,32 @@ __device__ __forceinline__ void tma_wait_read() {
 }
 __device__ __forceinline__ void tma_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
+// ------------------------------------------------------------------ tensor memory (TMEM) as an I/O staging store
+// 512 columns x 128 lanes x 32 bit per SM.  A warp reaches the 32 lanes of quadrant (warp id % 4); thread i of the warp is
+// lane base + i; address = lane << 16 | column.  Measured here: 128 KB written in 127 ns, read in 174 ns per SM
+// (tools/microbench/tmem_probe.cu) -- 3-4x shared memory -- so parking a tile costs next to nothing.
+__device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_ld4(uint32_t a, float &r0, float &r1, float &r2, float &r3) {
+    uint32_t u0, u1, u2, u3;
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(u0), "=r"(u1), "=r"(u2), "=r"(u3) : "r"(a) : "memory");
+    r0 = __uint_as_float(u0); r1 = __uint_as_float(u1); r2 = __uint_as_float(u2); r3 = __uint_as_float(u3);
+}
+__device__ __forceinline__ void tmem_st4(uint32_t a, float r0, float r1, float r2, float r3) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(__float_as_uint(r0)),
+                 "r"(__float_as_uint(r1)), "r"(__float_as_uint(r2)), "r"(__float_as_uint(r3)) : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void helper_bar() { asm volatile("bar.sync 2, 128;" ::: "memory"); }
+
 // landing-buffer element (one tile element as TMA delivers it: CH consecutive channels of one row)
 template <int MODE, class IO>
 struct Lin;
@@ -511,12 +543,20 @@ constexpr int kProducerThreads = 128;
 // CTAs with fewer compute threads keep the producer duties on compute thread 0 (an extra warpgroup would cost them
 // occupancy and registers)
 constexpr int kSepProducerMinThreads = 256;
+__host__ __device__ constexpr int helper_regs(int nt, int minb);
 __host__ __device__ constexpr int reg_floor8(int r) { return r / 8 * 8; }
 // register budget of the compute warps after the hand-over (launch allocation = nominal * all threads)
+// what is left per helper thread once the compute warps took their share
+__host__ __device__ constexpr int helper_regs_raw(int nt, int minb, int creg) {
+    return reg_floor8((reg_floor8(65536 / (minb * (nt + kProducerThreads))) * (nt + kProducerThreads) - creg * nt) / kProducerThreads);
+}
 __host__ __device__ constexpr int compute_regs(int nt, int minb) {
     return reg_floor8((reg_floor8(65536 / (minb * (nt + kProducerThreads))) * (nt + kProducerThreads) - 24 * kProducerThreads) / nt) > 128
                ? 128
                : reg_floor8((reg_floor8(65536 / (minb * (nt + kProducerThreads))) * (nt + kProducerThreads) - 24 * kProducerThreads) / nt);
+}
+__host__ __device__ constexpr int helper_regs(int nt, int minb) {
+    return helper_regs_raw(nt, minb, compute_regs(nt, minb)) < 24 ? 24 : helper_regs_raw(nt, minb, compute_regs(nt, minb));
 }
 
 // gate row -> registers (all loads in flight), registers -> padded shared table
@@ -553,7 +593,7 @@ __device__ __forceinline__ void cta_sync() {
 // spectrum.  TMA_IN: the tile is brought into shared memory by TMA (cp.async.bulk.tensor) and the CTA's next
 // tile is prefetched into L2 by the TMA unit; otherwise stage 0 loads straight from global into registers.
 template <class PL, int MODE, int NCOL, int NT, int MINB, class TIN, class TOUT, bool HAS_MEM, bool RFFT_ONLY = false,
-          bool TMA_IN = false>
+          bool TMA_IN = false, bool TMEM_IO = false>
 __global__ void __launch_bounds__(NT + ((TMA_IN && NT >= kSepProducerMinThreads) ? kProducerThreads : 0), MINB)
     spectre_mix_kernel(const MixParams p, const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_out) {
     using E = Elem<MODE>;
@@ -585,6 +625,18 @@ __global__ void __launch_bounds__(NT + ((TMA_IN && NT >= kSepProducerMinThreads)
     unsigned char *stg = smem_raw + bar_off + SM::bar_bytes;
     constexpr int NW = NT / 32;
     constexpr bool SEP = TMA_IN && (NT >= kSepProducerMinThreads);   // separate producer warpgroup
+    // TMEM layout of a parked tile: the tile as a flat array of elements e = row * NCOL + col (16 bytes each), element e in
+    // lane e % 128, columns 4 * (e / 128) .. +3.  Helper threads then touch consecutive 16-byte slots of the ring (no bank
+    // conflicts) and a compute thread finds all 16 inputs of its stage-0 butterfly in its own lane.
+    // TMEM_IO: the helper warpgroup parks the NEXT tile in tensor memory while this one is transformed and drains the
+    // PREVIOUS tile's results from tensor memory, so loads, stores and the FFT passes of three tiles overlap although
+    // shared memory holds only one.  Needs one stage-0 butterfly per thread and row blocks that are multiples of 128.
+    static_assert(!TMEM_IO || (SEP && sizeof(TIN) == 4 && sizeof(TOUT) == 4 && NT == NCOL * PL::L(0) && PL::L(0) % 128 == 0 &&
+                               MINB == 1 && (PL::N * NCOL * 4) % 128 == 0 && PL::N * NCOL * 4 / 128 * 2 <= 512),
+                  "TMEM staging: unsupported shape");
+    constexpr int G128 = PL::L(0) / 128;                 // 128-row groups per stage-0 row block (column-group stride per m = G128 * NCOL)
+    constexpr int CPR = NCOL * 4;                        // TMEM columns per tile row (fp32 channels)
+    constexpr int TCOLS = PL::N / 128 * CPR;             // TMEM columns of one parked tile (256 at 4096 x 8 ch)
     const int tid = threadIdx.x;
     for (int i = tid; i < TwPolicy<PL>::SMEM_N; i += NT) tw[i] = p.tw[PL::TWOFF(TwPolicy<PL>::FROM) + i];
     // first __syncthreads of the tile loop publishes the table
@@ -636,7 +688,124 @@ __global__ void __launch_bounds__(NT + ((TMA_IN && NT >= kSepProducerMinThreads)
         if (rnd_p >= 1) mbar_arrive(bar_stg_free + 8 * (kbuf ^ 1));
         ++rnd_p;
     };
-    if constexpr (TMA_IN) {
+    // ---------------------------------------------------------------- TMEM-staged variant: set-up + helper warpgroup
+    // barriers:  +0 tile parked in TMEM-IN (helper)   +8 TMEM-IN consumed (NW warps)   +16 results parked in TMEM-OUT (NW warps)
+    //            +24 TMEM-OUT drained (helper)   +32.. ring slot landed (TMA tx, kTmemSlots of them)   +96 TMEM base address
+    // ring (the staging area): kTmemSlots slots of one 256-row TMA box each, used for loads while parking and for
+    // stores while draining
+    [[maybe_unused]] uint32_t tmem_base = 0;
+    if constexpr (TMEM_IO) {
+        constexpr uint32_t SLOTB = (uint32_t)kTmaBoxRows * ROWB;           // bytes of one ring slot
+        const uint32_t bar_in_full = bar, bar_in_free = bar + 8, bar_out_full = bar + 16, bar_out_free = bar + 24,
+                       bar_landed = bar + 32;
+        uint32_t *tmem_base_s = reinterpret_cast<uint32_t *>(smem_raw + bar_off + 96);
+        if (tid == NT) {
+            mbar_init(bar_in_full, 1);
+            mbar_init(bar_in_free, NW);
+            mbar_init(bar_out_full, NW);
+            mbar_init(bar_out_free, 1);
+#pragma unroll
+            for (int i = 0; i < kTmemSlots; ++i) mbar_init(bar_landed + 8 * i, 1);
+        }
+        if (tid >= NT && tid < NT + 32) tmem_alloc(smem_u32(tmem_base_s), 512);   // helper warp 0 owns the allocation
+        tc_fence_before();
+        __syncthreads();
+        tc_fence_after();
+        tmem_base = *tmem_base_s;
+        if (tid >= NT) {
+            asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(helper_regs(NT, MINB)));
+            const int hl = tid - NT;                              // 0..127 = TMEM lane this helper thread serves
+            const uint32_t tq = tmem_base + ((uint32_t)(hl & ~31) << 16);
+            uint32_t land_cnt = 0;                                // boxes consumed so far (slot = cnt % slots, phase = cnt / slots)
+            uint32_t store_cnt = 0;                               // TMA store groups committed by the elected thread
+            constexpr int NBOX = N / kTmaBoxRows;
+            auto issue_box = [&](int tb, int tc, int k, uint32_t seq) {   // elected thread: box k of a tile -> slot seq % slots
+                const uint32_t sl = seq % kTmemSlots;
+                fence_proxy_async();
+                mbar_expect_tx(bar_landed + 8 * sl, SLOTB);
+                tma_load_3d(smem_u32(stg) + sl * SLOTB, &tmap, tc, k * kTmaBoxRows, tb, bar_landed + 8 * sl);
+            };
+            // park tile t in TMEM-IN: TMA boxes through the load slots (kTmemSlots - 1 boxes always in flight),
+            // two rows per helper thread and box
+            auto park_tile = [&](int t) {
+                const int tb = t / p.tiles_per_row;
+                const int tc = (t - tb * p.tiles_per_row) * NCOL * CH;
+                if (hl == 0) {
+                    tma_wait_read<0>();                            // stores of the previous drain have left the ring
+#pragma unroll
+                    for (int k = 0; k < kTmemSlots - 1; ++k) issue_box(tb, tc, k, land_cnt + k);
+                }
+#pragma unroll 1
+                for (int k = 0; k < NBOX; ++k) {
+                    // the slot box k + slots - 1 goes to was emptied before the helper barrier of the previous iteration
+                    if (hl == 0 && k + kTmemSlots - 1 < NBOX) issue_box(tb, tc, k + kTmemSlots - 1, land_cnt + kTmemSlots - 1);
+                    const uint32_t sl = land_cnt % kTmemSlots;
+                    mbar_wait(bar_landed + 8 * sl, (land_cnt / kTmemSlots) & 1);
+                    ++land_cnt;
+                    const float4 *slot = reinterpret_cast<const float4 *>(stg + sl * SLOTB);
+                    constexpr int GPB = kTmaBoxRows * NCOL / 128;  // 128-element groups per box
+                    float4 v[GPB];
+#pragma unroll
+                    for (int g = 0; g < GPB; ++g) v[g] = slot[g * 128 + hl];      // consecutive lanes, consecutive slots
+#pragma unroll
+                    for (int g = 0; g < GPB; ++g) tmem_st4(tq + (uint32_t)(4 * (k * GPB + g)), v[g].x, v[g].y, v[g].z, v[g].w);
+                    helper_bar();                                  // every helper thread has read this slot
+                }
+                tmem_wait_st();
+                tc_fence_before();
+                helper_bar();
+                if (hl == 0) mbar_arrive(bar_in_full);
+            };
+            // drain tile t from TMEM-OUT through the two store slots
+            auto drain_tile = [&](int t) {
+                const int tb = t / p.tiles_per_row;
+                const int tc = (t - tb * p.tiles_per_row) * NCOL * CH;
+#pragma unroll 1
+                for (int k = 0; k < NBOX; ++k) {
+                    const int s = k % kTmemSlots;
+                    if (hl == 0 && k >= kTmemSlots) tma_wait_read<kTmemSlots - 1>();   // the store that last used slot s has left it   // the store that last used slot s has left it
+                    helper_bar();
+                    float4 *slot = reinterpret_cast<float4 *>(stg + s * SLOTB);
+                    constexpr int GPB = kTmaBoxRows * NCOL / 128;
+                    float4 v[GPB];
+#pragma unroll
+                    for (int g = 0; g < GPB; ++g) tmem_ld4(tq + (uint32_t)(TCOLS + 4 * (k * GPB + g)), v[g].x, v[g].y, v[g].z, v[g].w);
+                    tmem_wait_ld();
+#pragma unroll
+                    for (int g = 0; g < GPB; ++g) slot[g * 128 + hl] = v[g];
+                    fence_proxy_async();
+                    helper_bar();
+                    if (hl == 0) {
+                        tma_store_3d(&tmap_out, smem_u32(slot), tc, k * kTmaBoxRows, tb);
+                        tma_commit();
+                        ++store_cnt;
+                    }
+                }
+                tc_fence_before();
+                helper_bar();
+                if (hl == 0) mbar_arrive(bar_out_free);            // TMEM-OUT may be overwritten (stores still draining smem)
+            };
+            int it = 0;
+            if ((int)blockIdx.x < p.num_tiles) park_tile(blockIdx.x);
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+                const int nt = tile + gridDim.x;
+                if (nt < p.num_tiles) {
+                    mbar_wait(bar_in_free, it & 1);               // the compute warps have pulled `tile` out of TMEM-IN
+                    tc_fence_after();
+                    park_tile(nt);
+                    // and let the TMA unit pull the tile after that one into L2 (requests only, no shared memory needed)
+                    if (p.prefetch && hl == 0 && nt + (int)gridDim.x < p.num_tiles) prefetch_tile(nt + gridDim.x);
+                }
+                mbar_wait(bar_out_full, it & 1);                  // results of `tile` are parked in TMEM-OUT
+                tc_fence_after();
+                drain_tile(tile);
+            }
+            if (hl == 0) tma_wait_all();
+        } else {
+            asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(compute_regs(NT, MINB)));
+        }
+    }
+    if constexpr (TMA_IN && !TMEM_IO) {
         if (tid == (SEP ? NT : 0)) {
             mbar_init(bar, 1);
             mbar_init(bar_buf_free, NW);
@@ -666,6 +835,7 @@ __global__ void __launch_bounds__(NT + ((TMA_IN && NT >= kSepProducerMinThreads)
             asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(compute_regs(NT, MINB)));
         }
     }
+    if (!TMEM_IO || tid < NT) {
     int tile_it = 0;
     uint32_t parity = 0;
     int tl_tile = 0;
@@ -673,6 +843,20 @@ __global__ void __launch_bounds__(NT + ((TMA_IN && NT >= kSepProducerMinThreads)
     if (p.timeline && tid == 0 && tl_tile < kTimelineTiles)                                              \
         p.timeline[((size_t)blockIdx.x * kTimelineTiles + tl_tile) * kTimelineSlots + (slot)] = globaltimer_ns();
     uint32_t rnd = 0;   // output staging rounds issued so far (buffer = rnd & 1)
+    // stage-0 butterfly of (thread, iteration): channel column and row offset u.  The TMEM variant ties u to the TMEM lane
+    // the thread can reach: lane = 32 * (warp % 4) + lane id = u mod 128.
+    auto map0 = [&](int it, int &col, int &u) {
+        if constexpr (TMEM_IO) {
+            // flat element index e = row * NCOL + col lives in TMEM lane e % 128: this thread's lane fixes (col, u mod 128/NCOL)
+            const int wq = tid >> 5, tl = 32 * (wq & 3) + (tid & 31);
+            col = tl % NCOL;
+            u = tl / NCOL + (128 / NCOL) * (wq >> 2);
+        } else {
+            const int w = tid + it * NT;
+            col = w % NCOL;
+            u = w / NCOL;
+        }
+    };
 
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         const int b = tile / p.tiles_per_row;
@@ -700,7 +884,23 @@ __global__ void __launch_bounds__(NT + ((TMA_IN && NT >= kSepProducerMinThreads)
         // ---- forward stage 0: (TMA landing buffer | global) -> butterfly -> twiddle -> padded column layout
         {
             Cx<V> x0[ITERS0][R0];
-            if constexpr (TMA_IN) {
+            if constexpr (TMEM_IO) {
+                // the helper warpgroup parked this tile in TMEM-IN: row u + L0 m sits in lane u % 128, column group
+                // (u / 128 + G128 m); this warp's 32 lanes are exactly its 32 values of u
+                mbar_wait(bar, tile_it & 1);
+                tc_fence_after();
+                SPX_MARK(1)
+                int col, u;
+                map0(0, col, u);
+                const uint32_t ta = tmem_base + ((uint32_t)(32 * ((tid >> 5) & 3)) << 16) + (uint32_t)(4 * ((u * NCOL + col) >> 7));
+#pragma unroll
+                for (int m = 0; m < R0; ++m)
+                    tmem_ld4(ta + (uint32_t)(m * G128 * CPR), x0[0][m].re.x, x0[0][m].re.y, x0[0][m].im.x, x0[0][m].im.y);
+                tmem_wait_ld();
+                tc_fence_before();
+                __syncwarp();
+                if ((tid & 31) == 0) mbar_arrive(bar + 8);   // TMEM-IN consumed by this warp
+            } else if constexpr (TMA_IN) {
                 mbar_wait(bar, parity);
                 parity ^= 1;
                 SPX_MARK(1)
@@ -708,7 +908,8 @@ __global__ void __launch_bounds__(NT + ((TMA_IN && NT >= kSepProducerMinThreads)
 #pragma unroll
                 for (int it = 0; it < ITERS0; ++it) {
                     const int w = tid + it * NT;
-                    const int col = w % NCOL, u = w / NCOL;
+                    int col, u;
+                    map0(it, col, u);
                     if (ITEMS0 % NT == 0 || w < ITEMS0) {
 #pragma unroll
                         for (int m = 0; m < R0; ++m) x0[it][m] = Lin<MODE, TIN>::get(lin[(u + m * L0) * NCOL + col]);
@@ -720,7 +921,8 @@ __global__ void __launch_bounds__(NT + ((TMA_IN && NT >= kSepProducerMinThreads)
 #pragma unroll
                 for (int it = 0; it < ITERS0; ++it) {
                     const int w = tid + it * NT;
-                    const int col = w % NCOL, u = w / NCOL;
+                    int col, u;
+                    map0(it, col, u);
                     if (ITEMS0 % NT == 0 || w < ITEMS0) {
                         const TIN *vp = vb + (long long)u * p.v_sn + col * CH;
                         if (full_tile) {
@@ -746,7 +948,8 @@ __global__ void __launch_bounds__(NT + ((TMA_IN && NT >= kSepProducerMinThreads)
 #pragma unroll
             for (int it = 0; it < ITERS0; ++it) {
                 const int w = tid + it * NT;
-                const int col = w % NCOL, u = w / NCOL;
+                int col, u;
+                map0(it, col, u);
                 if (ITEMS0 % NT == 0 || w < ITEMS0) {
                     Dft<R0, V>::run(x0[it]);
 #pragma unroll
@@ -762,6 +965,9 @@ __global__ void __launch_bounds__(NT + ((TMA_IN && NT >= kSepProducerMinThreads)
         }
         cta_sync<NT, SEP>();
         SPX_MARK(2)
+        // stagger: with every warp in lock step all of them load, then all compute, then all store; holding back two of
+        // the four warps of each scheduler lets their shared-memory phases overlap the others' butterflies
+        if (p.skew_ns > 0 && ((tid >> 7) & 1)) __nanosleep(p.skew_ns);
 
         // ---- forward stages 1 .. NS-2: smem -> butterfly -> twiddle -> smem (in place)
         // The exchange between stage NS-2 and the middle pass is a 16x16 transpose among the 16 threads that share
@@ -850,14 +1056,18 @@ __global__ void __launch_bounds__(NT + ((TMA_IN && NT >= kSepProducerMinThreads)
 #pragma unroll
             for (int it = 0; it < ITERS0; ++it) {
                 const int w = tid + it * NT;
-                const int col = w % NCOL, u = w / NCOL;
+                int col, u;
+                map0(it, col, u);
                 if (ITEMS0 % NT == 0 || w < ITEMS0) {
                     const S *cb = buf + col * CS + u + (u >> 4);
 #pragma unroll
                     for (int q = 0; q < R0; ++q) x0[it][q] = cswap(E::unpack(cb[q * L0 + ((q * L0) >> 4)]));
                 }
             }
-            if constexpr (TMA_IN) {
+            if constexpr (TMEM_IO) {
+                // the next tile's stage 0 writes this buffer as soon as a warp gets there: everyone must have read first
+                cta_sync<NT, SEP>();
+            } else if constexpr (TMA_IN) {
                 // this warp's share of the tile now lives in registers; when all warps have said so the producer
                 // hands the buffer to the TMA unit for the next tile
                 fence_proxy_async();
@@ -871,7 +1081,9 @@ __global__ void __launch_bounds__(NT + ((TMA_IN && NT >= kSepProducerMinThreads)
 #pragma unroll
             for (int it = 0; it < ITERS0; ++it) {
                 const int w = tid + it * NT;
-                const int u = w / NCOL;
+                int col, u;
+                map0(it, col, u);
+                (void)col;
                 if (ITEMS0 % NT == 0 || w < ITEMS0) {
 #pragma unroll
                     for (int q = 1; q < R0; ++q) {
@@ -882,7 +1094,25 @@ __global__ void __launch_bounds__(NT + ((TMA_IN && NT >= kSepProducerMinThreads)
                 }
             }
             SPX_MARK(6)
-            if constexpr (TMA_IN) {
+            if constexpr (TMEM_IO) {
+                // park the results in TMEM-OUT (same lane / column-group geometry as the input side); the helper
+                // warpgroup drains them to HBM while this CTA already transforms the next tile
+                if (tile_it >= 1) mbar_wait(bar + 24, (tile_it - 1) & 1);   // previous tile's results have been drained
+                tc_fence_after();
+                int col, u;
+                map0(0, col, u);
+                const uint32_t ta = tmem_base + ((uint32_t)(32 * ((tid >> 5) & 3)) << 16) +
+                                    (uint32_t)(TCOLS + 4 * ((u * NCOL + col) >> 7));
+#pragma unroll
+                for (int m = 0; m < R0; ++m) {
+                    const Cx<V> y = cswap(x0[0][m]);
+                    tmem_st4(ta + (uint32_t)(m * G128 * CPR), y.re.x, y.re.y, y.im.x, y.im.y);
+                }
+                tmem_wait_st();
+                tc_fence_before();
+                __syncwarp();
+                if ((tid & 31) == 0) mbar_arrive(bar + 16);   // results parked
+            } else if constexpr (TMA_IN) {
                 // results leave through two shared staging buffers (STG_MB row blocks each) and TMA stores; a buffer is
                 // refilled only after the TMA unit has read it (mbarrier `free`), so stores of one round overlap the
                 // fill of the next and the landing of the next tile
@@ -897,7 +1127,8 @@ __global__ void __launch_bounds__(NT + ((TMA_IN && NT >= kSepProducerMinThreads)
 #pragma unroll
                     for (int it = 0; it < ITERS0; ++it) {
                         const int w = tid + it * NT;
-                        const int col = w % NCOL, u = w / NCOL;
+                        int col, u;
+                        map0(it, col, u);
                         if (ITEMS0 % NT == 0 || w < ITEMS0) {
 #pragma unroll
                             for (int mm = 0; mm < MB; ++mm)
@@ -916,7 +1147,8 @@ __global__ void __launch_bounds__(NT + ((TMA_IN && NT >= kSepProducerMinThreads)
 #pragma unroll
                 for (int it = 0; it < ITERS0; ++it) {
                     const int w = tid + it * NT;
-                    const int col = w % NCOL, u = w / NCOL;
+                    int col, u;
+                    map0(it, col, u);
                     if (ITEMS0 % NT == 0 || w < ITEMS0) {
                         TOUT *op = ob + (long long)u * p.o_sn + col * CH;
                         if (full_tile) {
@@ -940,6 +1172,13 @@ __global__ void __launch_bounds__(NT + ((TMA_IN && NT >= kSepProducerMinThreads)
 #undef SPX_MARK
     if constexpr (TMA_IN && !SEP) {
         if (tid == 0) tma_wait_all();   // staging buffers must outlive the last TMA stores
+    }
+    }   // compute threads
+    if constexpr (TMEM_IO) {
+        tc_fence_before();
+        __syncthreads();                // every TMEM access of this CTA is done
+        tc_fence_after();
+        if (tid >= NT && tid < NT + 32) tmem_dealloc(tmem_base, 512);
     }
 }
 

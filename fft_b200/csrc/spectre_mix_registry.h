@@ -17,13 +17,14 @@ struct KernelEntry {
     int threads;
     int minb;
     int twn;       // twiddle table entries
-    size_t (*smem_bytes)(int gate_tables, bool tma);
+    size_t (*smem_bytes)(int gate_tables, bool tma, bool tmem);
     int out_box_rows;   // rows per TMA store box (TMA variant)
     // tmap != nullptr selects the TMA-fed variant (only when tma_ok)
     cudaError_t (*launch)(const MixParams &p, int grid, bool has_mem, const CUtensorMap *tmap_in, const CUtensorMap *tmap_out,
-                          cudaStream_t st);
-    int (*occupancy)(int gate_tables, bool has_mem, bool tma);
+                          bool tmem, cudaStream_t st);
+    int (*occupancy)(int gate_tables, bool has_mem, bool tma, bool tmem);
     int tma_ok;    // 1: a TMA-fed variant exists (packed mode, landed row >= 16 bytes)
+    int tmem_ok;   // 1: a TMEM-staged variant exists (tile I/O parked in tensor memory by a helper warpgroup)
     // forward half only (half spectrum out); MODE_REAL variants only, else nullptr
     cudaError_t (*launch_rfft)(const MixParams &p, int grid, cudaStream_t st);
 };
@@ -31,24 +32,28 @@ struct KernelEntry {
 template <class PL, int MODE, int NCOL, int NT, int MINB, class TIO>
 struct Launcher {
     using SM = Smem<PL, MODE, NCOL>;
-    static size_t smem_bytes(int gate_tables, bool tma) {
-        return SM::bytes(gate_tables, tma && kTma, sizeof(typename Lin<MODE, TIO>::T) * NCOL);
+    static size_t smem_bytes(int gate_tables, bool tma, bool tmem = false) {
+        return SM::bytes(gate_tables, tma && kTma, sizeof(typename Lin<MODE, TIO>::T) * NCOL, tma && tmem && kTmem);
     }
     // TMA delivers rows of NCOL elements; the box's inner extent must be a multiple of 16 bytes
     static constexpr bool kTma = (MODE == MODE_QUAD) && ((sizeof(TIO) * 4 * NCOL) % 16 == 0);
-    template <bool HAS_MEM, bool TMA>
+    // TMEM staging: fp32 packed tiles, one stage-0 butterfly per thread, 1 CTA per SM, two tiles fit the 512 columns
+    static constexpr bool kTmem = kTma && sizeof(TIO) == 4 && NT >= kSepProducerMinThreads && NT == NCOL * PL::L(0) &&
+                                  PL::L(0) % 128 == 0 && MINB == 1 && (PL::N * NCOL * 4 / 128 * 2 <= 512);
+    template <bool HAS_MEM, bool TMA, bool TMEM>
     static const void *fn() {
         return reinterpret_cast<const void *>(
-            &spectre_mix_kernel<PL, MODE, NCOL, NT, MINB, TIO, TIO, HAS_MEM, false, (TMA && kTma)>);
+            &spectre_mix_kernel<PL, MODE, NCOL, NT, MINB, TIO, TIO, HAS_MEM, false, (TMA && kTma), (TMA && TMEM && kTmem)>);
     }
-    static const void *pick(bool has_mem, bool tma) {
-        if (tma && kTma) return has_mem ? fn<true, true>() : fn<false, true>();
-        return has_mem ? fn<true, false>() : fn<false, false>();
+    static const void *pick(bool has_mem, bool tma, bool tmem = false) {
+        if (tma && tmem && kTmem) return has_mem ? fn<true, true, true>() : fn<false, true, true>();
+        if (tma && kTma) return has_mem ? fn<true, true, false>() : fn<false, true, false>();
+        return has_mem ? fn<true, false, false>() : fn<false, false, false>();
     }
     static cudaError_t launch(const MixParams &p, int grid, bool has_mem, const CUtensorMap *tmap, const CUtensorMap *tmap_out,
-                              cudaStream_t st) {
-        const size_t sm = smem_bytes(p.gate_tables, tmap != nullptr);
-        const void *f = pick(has_mem, tmap != nullptr);
+                              bool tmem, cudaStream_t st) {
+        const size_t sm = smem_bytes(p.gate_tables, tmap != nullptr, tmem);
+        const void *f = pick(has_mem, tmap != nullptr, tmem);
         // opt in to > 48 KB dynamic shared memory (cheap; the driver caches the attribute per function)
         cudaError_t e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
         if (e != cudaSuccess) return e;
@@ -60,7 +65,7 @@ struct Launcher {
     }
     static cudaError_t launch_rfft(const MixParams &p, int grid, cudaStream_t st) {
         static_assert(MODE == MODE_REAL, "rfft-only is built for MODE_REAL");
-        const size_t sm = smem_bytes(0, false);
+        const size_t sm = smem_bytes(0, false, false);
         const void *f = reinterpret_cast<const void *>(&spectre_mix_kernel<PL, MODE, NCOL, NT, MINB, TIO, TIO, false, true>);
         cudaError_t e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
         if (e != cudaSuccess) return e;
@@ -71,9 +76,9 @@ struct Launcher {
         void *args[] = {&pc, &tm, &tmo};
         return cudaLaunchKernel(f, dim3(grid), dim3(NT), args, sm, st);
     }
-    static int occupancy(int gate_tables, bool has_mem, bool tma) {
-        const size_t sm = smem_bytes(gate_tables, tma);
-        const void *f = pick(has_mem, tma);
+    static int occupancy(int gate_tables, bool has_mem, bool tma, bool tmem) {
+        const size_t sm = smem_bytes(gate_tables, tma, tmem);
+        const void *f = pick(has_mem, tma, tmem);
         if (cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm) != cudaSuccess) {
             cudaGetLastError();
             return 0;
@@ -107,6 +112,7 @@ struct RfftPtr<PL, MODE_REAL, NCOL, NT, MINB, TIO> {
             &::spx::Launcher<::spx::Plan<R0, R1, R2, R3>, MODE, NCOL, NT, MINB, TIO>::launch,                 \
             &::spx::Launcher<::spx::Plan<R0, R1, R2, R3>, MODE, NCOL, NT, MINB, TIO>::occupancy,              \
             ::spx::Launcher<::spx::Plan<R0, R1, R2, R3>, MODE, NCOL, NT, MINB, TIO>::kTma ? 1 : 0,            \
+            ::spx::Launcher<::spx::Plan<R0, R1, R2, R3>, MODE, NCOL, NT, MINB, TIO>::kTmem ? 1 : 0,           \
             ::spx::RfftPtr<::spx::Plan<R0, R1, R2, R3>, MODE, NCOL, NT, MINB, TIO>::get()                     \
     }
 

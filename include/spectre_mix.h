@@ -104,6 +104,13 @@ int spectre_mix_set_prefetch(int enable);
 /* Enable (default) / disable TMA-staged tile loads (falls back to direct 128-bit global loads).  For experiments only. */
 int spectre_mix_set_tma(int enable);
 
+/* Enable (default) / disable staging of tile I/O through tensor memory (TMEM) by a helper warpgroup, where a variant
+ * exists (n_fft = 4096 fp32).  For experiments only. */
+int spectre_mix_set_tmem(int enable);
+
+/* Experiment: hold back half of the warps by `ns` nanoseconds before the warp-local passes (0 = off). */
+int spectre_mix_set_skew_ns(int ns);
+
 /* Debug: device buffer of grid * 8 tiles * 8 uint64 that receives per-phase %globaltimer stamps (NULL = off). */
 int spectre_mix_set_timeline(void *device_buffer);
 

@@ -197,21 +197,25 @@ def test_tma_and_direct_load_paths_agree(fb, oracle, dev):
     """The TMA-staged tile load and the direct 128-bit global load feed the same arithmetic: bitwise equal."""
     from fft_b200 import _lib
     lib = _lib.load()
-    for (B, N, n_fft, C, dg) in [(3, 4096, 4096, 64, 16), (2, 900, 1024, 40, 8), (2, 2048, 2048, 32, 16)]:
+    for (B, N, n_fft, C, dg) in [(3, 4096, 4096, 64, 16), (40, 3500, 4096, 40, 8), (2, 900, 1024, 40, 8), (2, 2048, 2048, 32, 16)]:
         V, gate, mem = _rand_case(B, N, n_fft, C, dg, True, seed=21 + N)
         args = (V.to(dev), gate.to(dev), mem.to(dev))
         try:
             lib.spectre_mix_set_tma(0)
             y0 = fb.spectral_mix(*args, n_fft=n_fft, group_width=dg)
             lib.spectre_mix_set_tma(1)
-            lib.spectre_mix_set_prefetch(0)
+            lib.spectre_mix_set_tmem(0)
             y1 = fb.spectral_mix(*args, n_fft=n_fft, group_width=dg)
             lib.spectre_mix_set_prefetch(1)
             y2 = fb.spectral_mix(*args, n_fft=n_fft, group_width=dg)
+            lib.spectre_mix_set_prefetch(0)
+            lib.spectre_mix_set_tmem(1)          # tile I/O staged through tensor memory where a variant exists (4096 fp32)
+            y3 = fb.spectral_mix(*args, n_fft=n_fft, group_width=dg)
         finally:
             lib.spectre_mix_set_tma(1)
+            lib.spectre_mix_set_tmem(1)
             lib.spectre_mix_set_prefetch(1)
-        assert torch.equal(y0, y1) and torch.equal(y1, y2)
+        assert torch.equal(y0, y1) and torch.equal(y1, y2) and torch.equal(y1, y3)
         _check(y1, oracle.mix_flat(V, gate, n_fft, dg, mem).numpy())
 
 

@@ -19,10 +19,12 @@ ap.add_argument("--n-fft", type=int, default=4096)
 ap.add_argument("--batch", type=int, default=32)
 ap.add_argument("--prefetch", type=int, default=1)
 ap.add_argument("--tma", type=int, default=1)
+ap.add_argument("--tmem", type=int, default=1)
 a = ap.parse_args()
 lib = _lib.load()
 lib.spectre_mix_set_prefetch(a.prefetch)
 lib.spectre_mix_set_tma(a.tma)
+lib.spectre_mix_set_tmem(a.tmem)
 dev = torch.device("cuda")
 C, dg = 768, 16
 V = torch.randn(a.batch, a.n_fft, C, device=dev)

@@ -15,12 +15,13 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from fft_b200 import _lib  # noqa: E402
 
 
-def time_case(lib, n_fft, C, dg, B, tile, prefetch, dtype=torch.float32, mem=False, reps=10, N=None, tma=1):
+def time_case(lib, n_fft, C, dg, B, tile, prefetch, dtype=torch.float32, mem=False, reps=10, N=None, tma=1, tmem=1):
     dev = torch.device("cuda")
     N = N or n_fft
     lib.spectre_mix_set_tile_channels(tile)
     lib.spectre_mix_set_prefetch(prefetch)
     lib.spectre_mix_set_tma(tma)
+    lib.spectre_mix_set_tmem(tmem)
     gen = torch.Generator(device=dev).manual_seed(0)
     sets = 2
     V = [torch.randn(B, N, C, device=dev, generator=gen).to(dtype) for _ in range(sets)]
