@@ -22,6 +22,9 @@ SYMBOLS = (
     "spectre_mix_fwd",
     "spectre_mix_fwd_host",
     "spectre_rfft_fwd",
+    "spectre_decode_update",
+    "spectre_decode_readout",
+    "spectre_decode_step",
     "spectre_mix_plan",
     "spectre_mix_set_tile_channels",
     "spectre_mix_set_prefetch",
@@ -76,6 +79,12 @@ def load():
         lib.spectre_mix_fwd_host.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32]
         lib.spectre_rfft_fwd.restype = i32
         lib.spectre_rfft_fwd.argtypes = [vp, i32, i64, i64, vp, i32, i32, i32, i32, vp]
+        lib.spectre_decode_update.restype = i32
+        lib.spectre_decode_update.argtypes = [vp, vp, vp, i32, i32, ctypes.c_longlong, vp]
+        lib.spectre_decode_readout.restype = i32
+        lib.spectre_decode_readout.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp]
+        lib.spectre_decode_step.restype = i32
+        lib.spectre_decode_step.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, ctypes.c_longlong, vp]
         lib.spectre_mix_plan.restype = i32
         lib.spectre_mix_plan.argtypes = [i32, i32, i32, i32, i32, i32, i32, i32, ctypes.POINTER(PlanInfo)]
         lib.spectre_mix_set_tile_channels.restype = i32

@@ -1,0 +1,125 @@
+// spectre_decode.cu -- autoregressive decode side of the Spectre mixer.
+//
+// Replaces, for ALL heads of a layer at once (channels = embed_dim, gate row of channel c = c / group_width):
+//   * PrefixFFTCache.decode_step   spectre.py:795-806  running spectrum += e^{j w k t} v_t  (- e^{j w k j} v_old when evicting)
+//   * SpectreHead.decode_step      spectre.py:605      mixed_half = gate_broadcast * prefix_fft
+//   * pruned_irfft_single          spectre.py:614-655  one output sample of the inverse real FFT
+// as ONE bandwidth-bound pass over prefix_fft (F_half x d complex64): read, update, write, and reduce over k.
+//
+// The reference evaluates every phase angle in float32 (complex64 tensor arithmetic); the kernels reproduce that
+// rounding order so that results agree to float32 round-off rather than to the exact angles:
+//   cache phases   theta = fl(fl(w32 * k) * t),            w32 = fl32(-2 pi / n_fft)        (spectre.py:766, :801, :805)
+//   readout phase  phi   = fl(fl(fl(2pi32 * k) * pos) / n)                                   (spectre.py:628)
+// and keep the reference's Nyquist term contrib[-1] * (-1)^pos (spectre.py:650) as it is.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "../../include/spectre_mix.h"
+
+namespace {
+
+constexpr int kKChunk = 16;  // frequency bins per block
+
+// mode bit 0: update the spectrum; bit 1: read one output sample out
+template <int MODE>
+__global__ void __launch_bounds__(256) decode_kernel(float2 *__restrict__ prefix, const float *__restrict__ v_new,
+                                                     const float *__restrict__ v_old, const float2 *__restrict__ gate,
+                                                     float *__restrict__ out, int n_fft, int d, int group_width, float t_new,
+                                                     float t_old, int evict, int pos, float w32) {
+    const int c = blockIdx.y * blockDim.x + threadIdx.x;
+    if (c >= d) return;
+    const int F_half = n_fft / 2 + 1;
+    const int k0 = blockIdx.x * kKChunk;
+    const int k1 = min(k0 + kKChunk, F_half);
+    float vn = 0.f, vo = 0.f;
+    if (MODE & 1) {
+        vn = v_new[c];
+        if (evict) vo = v_old[c];
+    }
+    const float2 *grow = (MODE & 2) ? gate + (size_t)(c / group_width) * F_half : nullptr;
+    const float two_pi32 = (float)(2.0 * M_PI);
+    const float posf = (float)pos, nf = (float)n_fft;
+    const float nyq_sign = (pos & 1) ? -1.f : 1.f;
+    float acc = 0.f;
+    for (int k = k0; k < k1; ++k) {
+        float2 X = prefix[(size_t)k * d + c];
+        const float kf = (float)k;
+        if (MODE & 1) {
+            const float a = __fmul_rn(w32, kf);
+            if (evict) {   // spectre.py:799-802: subtract the evicted token first
+                float s, co;
+                sincosf(__fmul_rn(a, t_old), &s, &co);
+                X.x -= co * vo;
+                X.y -= s * vo;
+            }
+            float s, co;
+            sincosf(__fmul_rn(a, t_new), &s, &co);
+            X.x += co * vn;
+            X.y += s * vn;
+            prefix[(size_t)k * d + c] = X;
+        }
+        if (MODE & 2) {
+            const float2 g = grow[k];
+            const float yr = g.x * X.x - g.y * X.y;           // gate_broadcast * prefix_fft
+            const float yi = g.x * X.y + g.y * X.x;
+            float s, co;
+            sincosf(__fdiv_rn(__fmul_rn(__fmul_rn(two_pi32, kf), posf), nf), &s, &co);
+            const float contrib = yr * co - yi * s;
+            float wgt = 2.f;                                    // spectre.py:643-653
+            if (k == 0) wgt = 1.f;
+            else if (k == F_half - 1 && (n_fft % 2) == 0) wgt = nyq_sign;
+            acc += wgt * contrib;
+        }
+    }
+    if (MODE & 2) atomicAdd(out + c, acc / nf);
+}
+
+int launch(int mode, void *prefix, const float *v_new, const float *v_old, const void *gate, float *out, int n_fft, int d,
+           int group_width, long long t, int pos, cudaStream_t st) {
+    if (n_fft < 2 || d <= 0 || group_width <= 0 || (d % group_width) != 0) return SPECTRE_MIX_ERR_BAD_ARG;
+    const int F_half = n_fft / 2 + 1;
+    const int threads = d >= 256 ? 256 : ((d + 31) / 32) * 32;
+    dim3 grid((F_half + kKChunk - 1) / kKChunk, (d + threads - 1) / threads);
+    const float w32 = (float)(-2.0 * M_PI / (double)n_fft);
+    const long long j = t % n_fft;
+    const int evict = (t >= n_fft) ? 1 : 0;
+    if ((mode & 2) && out) {
+        cudaError_t e = cudaMemsetAsync(out, 0, sizeof(float) * (size_t)d, st);
+        if (e != cudaSuccess) return SPECTRE_MIX_ERR_CUDA + (int)e;
+    }
+    float2 *pf = reinterpret_cast<float2 *>(prefix);
+    const float2 *g = reinterpret_cast<const float2 *>(gate);
+    switch (mode) {
+        case 1: decode_kernel<1><<<grid, threads, 0, st>>>(pf, v_new, v_old, g, out, n_fft, d, group_width, (float)t, (float)j, evict, pos, w32); break;
+        case 2: decode_kernel<2><<<grid, threads, 0, st>>>(pf, v_new, v_old, g, out, n_fft, d, group_width, (float)t, (float)j, evict, pos, w32); break;
+        default: decode_kernel<3><<<grid, threads, 0, st>>>(pf, v_new, v_old, g, out, n_fft, d, group_width, (float)t, (float)j, evict, pos, w32); break;
+    }
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : SPECTRE_MIX_ERR_CUDA + (int)e;
+}
+
+}  // namespace
+
+extern "C" {
+
+int spectre_decode_update(void *prefix_fft, const float *v_new, const float *v_old, int n_fft, int d, long long t, void *stream) {
+    if (!prefix_fft || !v_new || (t >= n_fft && !v_old)) return SPECTRE_MIX_ERR_BAD_ARG;
+    return launch(1, prefix_fft, v_new, v_old, nullptr, nullptr, n_fft, d, 1, t, 0, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int spectre_decode_readout(const void *prefix_fft, const void *gate, float *out, int n_fft, int d, int group_width, int pos,
+                           void *stream) {
+    if (!prefix_fft || !gate || !out) return SPECTRE_MIX_ERR_BAD_ARG;
+    return launch(2, const_cast<void *>(prefix_fft), nullptr, nullptr, gate, out, n_fft, d, group_width, 0, pos,
+                  reinterpret_cast<cudaStream_t>(stream));
+}
+
+int spectre_decode_step(void *prefix_fft, const float *v_new, const float *v_old, const void *gate, float *out, int n_fft,
+                        int d, int group_width, long long t, void *stream) {
+    if (!prefix_fft || !v_new || !gate || !out || (t >= n_fft && !v_old)) return SPECTRE_MIX_ERR_BAD_ARG;
+    return launch(3, prefix_fft, v_new, v_old, gate, out, n_fft, d, group_width, t, (int)(t % n_fft),
+                  reinterpret_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

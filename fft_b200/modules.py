@@ -251,6 +251,12 @@ class SpectreHead(nn.Module):
                 memory_fft: Optional[torch.Tensor] = None):
         return head_forward(self, x, pos_phase, return_q_pool, memory_fft)
 
+    @torch.no_grad()
+    def decode_step(self, q_t: torch.Tensor, v_t: torch.Tensor, cache) -> torch.Tensor:
+        """Single-token decode (spectre.py:562-611) against a ``fft_b200.PrefixFFTCache``."""
+        from .decode import head_decode_step
+        return head_decode_step(self, q_t, v_t, cache)
+
 
 class SpectreMultiHead(nn.Module):
     """Several heads + out projection; constructor as spectre.py:664-676."""

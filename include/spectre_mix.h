@@ -79,6 +79,22 @@ int spectre_mix_fwd_host(const float *v, const float *gate, const float *mem, fl
 int spectre_rfft_fwd(const void *v, int v_dtype, int64_t v_stride_b, int64_t v_stride_n,
                      void *spec, int B, int N, int n_fft, int C, void *stream);
 
+/* ---- decode side: one bandwidth-bound pass over the running spectrum prefix_fft, complex64 [n_fft/2+1][d],
+ * for all heads of a layer (gate row of channel c = c / group_width).  t is the index of the token being added
+ * (PrefixFFTCache.t after its increment); when t >= n_fft the token at ring position t % n_fft is evicted and v_old
+ * must hold it.  Phase angles are evaluated in float32 in the reference's rounding order.
+ *
+ * spectre_decode_update   replaces PrefixFFTCache.decode_step's spectrum update, spectre.py:795-806
+ * spectre_decode_readout  replaces `gate_broadcast * prefix_fft` + pruned_irfft_single, spectre.py:605, :614-655;
+ *                         gate = complex64 [d/group_width][n_fft/2+1] (already multiplied by the positional phase of
+ *                         spectre.py:594-598), out = float32 [d], pos = output sample index
+ * spectre_decode_step     both in one pass: update with (v_new, v_old, t), then read sample t % n_fft out */
+int spectre_decode_update(void *prefix_fft, const float *v_new, const float *v_old, int n_fft, int d, long long t, void *stream);
+int spectre_decode_readout(const void *prefix_fft, const void *gate, float *out, int n_fft, int d, int group_width, int pos,
+                           void *stream);
+int spectre_decode_step(void *prefix_fft, const float *v_new, const float *v_old, const void *gate, float *out, int n_fft,
+                        int d, int group_width, long long t, void *stream);
+
 /* Tuning / introspection used by bench.py and the tests (not needed by a binding). */
 typedef struct spectre_mix_plan_info {
     int n_fft;

@@ -156,6 +156,24 @@ def main():
                         X_half=Xh.numpy(), pruned_pos=np.array([0, 1, 7, 255]), pruned=pr.numpy())
     print("decode_prefill_n256_d32 written")
 
+    # (9) decode sequence through the stock SpectreHead.decode_step + PrefixFFTCache (spectre.py:562-611, :786-814):
+    # prompt of 200 tokens, then 100 single-token steps (crosses t >= N = 256, so eviction is exercised)
+    torch.manual_seed(21)
+    head = ref.SpectreHead(32, 256, pooling_type="mean").eval()
+    cache = ref.PrefixFFTCache(256, 32, device=torch.device("cpu"))
+    with torch.no_grad():
+        xp = torch.randn(200, 32)
+        Qp, Vp = head.W_q(xp), head.W_v(xp)
+        cache.prefill(Qp, Vp)
+        xs = torch.randn(100, 32)
+        qs, vs = head.W_q(xs), head.W_v(xs)
+        outs = torch.stack([head.decode_step(qs[i], vs[i], cache) for i in range(100)])
+    d = {"sd::" + k: v.detach().numpy() for k, v in head.state_dict().items()}
+    d.update(Qp=Qp.numpy(), Vp=Vp.numpy(), qs=qs.numpy(), vs=vs.numpy(), outs=outs.numpy(),
+             prefix_fft=cache.prefix_fft.numpy(), sum_q=cache.sum_q.numpy(), t=np.int64(cache.t))
+    np.savez_compressed(os.path.join(OUT, "decode_seq_n256_d32.npz"), **d)
+    print("decode_seq_n256_d32 written", outs.shape)
+
 
 if __name__ == "__main__":
     main()

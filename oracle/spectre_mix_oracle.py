@@ -142,3 +142,18 @@ def pruned_irfft_single(X_half: torch.Tensor, n: int, pos: int) -> torch.Tensor:
     else:
         res = contrib[0] + 2 * contrib[1:].sum(0)
     return res / n
+
+
+def cache_update(prefix_fft: torch.Tensor, V_buf: torch.Tensor, v_t: torch.Tensor, t: int, n: int) -> None:
+    """In-place spectrum update of ``PrefixFFTCache.decode_step`` for token index t (``spectre.py:795-809``).
+
+    Same complex64 phase arithmetic as the reference: ``exp(1j * omega * freq_k * t)`` with float32 ``freq_k``.
+    """
+    import math
+    omega = -2 * math.pi / n
+    freq_k = torch.arange(n // 2 + 1, dtype=torch.float32)
+    j = t % n
+    if t >= n:
+        prefix_fft -= torch.exp(1j * omega * freq_k * j).unsqueeze(-1) * V_buf[j]
+    prefix_fft += torch.exp(1j * omega * freq_k * t).unsqueeze(-1) * v_t
+    V_buf[j] = v_t

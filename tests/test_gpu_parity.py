@@ -319,3 +319,42 @@ def test_multihead_matches_per_head_calls(fb, dev):
                     for h, c, m in zip(mh.heads, torch.chunk(x, 4, -1), torch.chunk(mem, 4, -1))]
         loop = mh.out_proj(torch.cat(per_head, dim=-1))
     assert (fused - loop).norm() / loop.norm() < 1e-5
+
+
+# --------------------------------------------------------------------------- decode side
+def test_decode_sequence_matches_reference(fb, dev):
+    """Prompt of 200 tokens then 100 single-token steps (eviction after t >= 256) against the outputs of the stock
+    SpectreHead.decode_step / PrefixFFTCache recorded from the reference (spectre.py:562-611, :786-814)."""
+    g = load_golden("decode_seq_n256_d32")
+    head = fb.SpectreHead(32, 256, pooling_type="mean")
+    head.load_state_dict({k[4:]: torch.from_numpy(v) for k, v in g.items() if k.startswith("sd::")}, strict=True)
+    head = head.to(dev).eval()
+    cache = fb.PrefixFFTCache(256, 32, device=dev)
+    cache.prefill(torch.from_numpy(g["Qp"]).to(dev), torch.from_numpy(g["Vp"]).to(dev))
+    qs, vs = torch.from_numpy(g["qs"]).to(dev), torch.from_numpy(g["vs"]).to(dev)
+    outs = torch.stack([head.decode_step(qs[i], vs[i], cache) for i in range(qs.shape[0])]).cpu().numpy()
+    assert cache.t == int(g["t"])
+    assert rel_l2(outs, g["outs"]) < 2e-5 and max_abs_rel(outs, g["outs"]) < 1e-4
+    got = torch.view_as_real(cache.prefix_fft).cpu().numpy()
+    want = np.ascontiguousarray(g["prefix_fft"]).view(np.float32).reshape(got.shape)
+    assert rel_l2(got, want) < 1e-5
+    assert rel_l2(cache.sum_q.cpu().numpy(), g["sum_q"]) < 1e-5
+
+
+def test_decode_split_equals_fused(fb, dev):
+    """cache.decode_step + cache.readout (two kernels) == the fused step; several heads share one cache (d = 64, d_g = 8)."""
+    torch.manual_seed(30)
+    n, d, dg = 128, 64, 8
+    c1, c2 = fb.PrefixFFTCache(n, d, device=dev), fb.PrefixFFTCache(n, d, device=dev)
+    Q, V = torch.randn(100, d, device=dev), torch.randn(100, d, device=dev)
+    c1.prefill(Q, V)
+    c2.prefill(Q, V)
+    for step in range(60):
+        q, v = torch.randn(d, device=dev), torch.randn(d, device=dev)
+        gate = torch.randn(d // dg, n // 2 + 1, dtype=torch.cfloat, device=dev)
+        c1.decode_step(q, v)
+        a = c1.readout(gate, c1.t % n)
+        v_old, _ = c2._advance(q, v)
+        b = c2.fused_step(v, v_old, gate)
+        assert torch.allclose(a, b, rtol=1e-5, atol=1e-5)
+    assert torch.equal(c1.prefix_fft, c2.prefix_fft)

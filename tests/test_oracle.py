@@ -109,3 +109,19 @@ def test_decode_restatements_match_reference_goldens():
     for p, want in zip(g["pruned_pos"], g["pruned"]):
         got = oracle.pruned_irfft_single(_t(g["X_half"]), 256, int(p)).numpy()
         assert np.allclose(got, want, rtol=1e-5, atol=1e-6)
+
+
+def test_cache_update_restatement_matches_reference_sequence():
+    """Replay the reference's 100 decode steps (with eviction) through the oracle's spectrum update."""
+    g = load_golden("decode_seq_n256_d32")
+    n = 256
+    Vp, vs = _t(g["Vp"]), _t(g["vs"])
+    prefix = oracle.prefill_spectrum(Vp, n)
+    V_buf = torch.zeros(n, Vp.shape[1])
+    V_buf[: Vp.shape[0]] = Vp
+    t = Vp.shape[0] - 1
+    for i in range(vs.shape[0]):
+        t += 1
+        oracle.cache_update(prefix, V_buf, vs[i], t, n)
+    assert t == int(g["t"])
+    assert np.array_equal(prefix.numpy(), g["prefix_fft"])
