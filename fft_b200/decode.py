@@ -56,9 +56,12 @@ class PrefixFFTCache:
         j = self.t % self.N
         v_old = self.V_buf[j].clone()
         self.V_buf[j] = v_t
-        q_old = self.Q_buf[j].clone()
         self.Q_buf[j] = q_t
-        self.sum_q = self.sum_q + q_t - (q_old if self.t >= self.N else 0.0)
+        # spectre.py:810-813 takes `q_old = self.Q_buf[j]` as a VIEW, overwrites the slot, then adds `q_t - q_old`:
+        # once the window is full (t >= N) that difference is identically zero, i.e. the running query sum stops
+        # moving.  Results must match the reference, so the same happens here.
+        if self.t < self.N:
+            self.sum_q = self.sum_q + q_t
         return v_old, j
 
     def decode_step(self, q_t: torch.Tensor, v_t: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
