@@ -12,6 +12,7 @@ without the CUDA library or a GPU raises.
 """
 from .ops import rfft_seq, spectral_mix, spectral_mix_host, plan_info  # noqa: F401
 from .decode import PrefixFFTCache, decode_gate, head_decode_step  # noqa: F401
+from .model import SpectreBase  # noqa: F401
 from .modules import (  # noqa: F401
     ComplexModReLU,
     SpectreBlock,
@@ -25,5 +26,5 @@ from .modules import (  # noqa: F401
 __all__ = [
     "spectral_mix", "spectral_mix_host", "rfft_seq", "plan_info",
     "SpectreHead", "SpectreMultiHead", "SpectreBlock", "WaveletRefinement", "ComplexModReLU",
-    "interp_complex_1d", "patch_reference", "PrefixFFTCache", "head_decode_step", "decode_gate",
+    "interp_complex_1d", "patch_reference", "PrefixFFTCache", "head_decode_step", "decode_gate", "SpectreBase",
 ]

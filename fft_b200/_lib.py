@@ -32,6 +32,7 @@ SYMBOLS = (
     "spectre_mix_set_timeline",
     "spectre_mix_set_tmem",
     "spectre_mix_set_skew_ns",
+    "spectre_mix_set_two_pass",
 )
 
 
@@ -93,6 +94,8 @@ def load():
         lib.spectre_mix_set_prefetch.argtypes = [i32]
         lib.spectre_mix_set_tma.restype = i32
         lib.spectre_mix_set_tma.argtypes = [i32]
+        lib.spectre_mix_set_two_pass.restype = i32
+        lib.spectre_mix_set_two_pass.argtypes = [i32]
         lib.spectre_mix_set_skew_ns.restype = i32
         lib.spectre_mix_set_skew_ns.argtypes = [i32]
         lib.spectre_mix_set_tmem.restype = i32

@@ -17,6 +17,7 @@
 #include <vector>
 
 #include "../../include/spectre_mix.h"
+#include "spectre_long.h"
 #include "spectre_mix_registry.h"
 
 namespace {
@@ -45,6 +46,7 @@ int g_prefetch = 1;   // L2 prefetch of the tile after next by the TMA unit (hel
 int g_use_tma = 1;
 int g_use_tmem = 1;
 int g_skew_ns = 0;
+int g_use_two_pass = 1;
 unsigned long long *g_timeline = nullptr;
 
 // ---------------------------------------------------------------- kernel registry
@@ -71,6 +73,8 @@ struct DeviceState {
     int sm_count = 0;
     int max_smem_optin = 0;
     std::map<int, float2 *> twiddles;          // n_fft -> device table
+    void *scratch = nullptr;                   // long-context two-pass path: intermediate [B][R][4096][C] fp32
+    size_t scratch_bytes = 0;
     std::map<std::pair<const KernelEntry *, int>, int> occupancy;  // (entry, gate_tables*2+has_mem) -> CTAs/SM
 };
 std::mutex g_mu;
@@ -169,7 +173,7 @@ int choose(const DeviceState &st, int n_fft, int dtype, int mode_max, int C, int
         const KernelEntry *best = nullptr;
         Choice bc;
         for (const KernelEntry &k : reg) {
-            if (k.n_fft != n_fft || k.io != dtype || k.mode != mode) continue;
+            if (k.n_fft != n_fft || k.io != dtype || k.mode != mode || k.sub) continue;
             const int ch = mode_channels(mode);
             const int tw = ch * k.ncol;  // channels per tile
             if (g_tile_channels_override && tw != g_tile_channels_override) continue;
@@ -260,6 +264,79 @@ bool make_v_tensor_map(CUtensorMap *tm, const void *v, int dtype, long long v_sb
     return r == CUDA_SUCCESS;
 }
 
+
+// ---------------------------------------------------------------- long-context two-pass path (n_fft = 8192, 16384)
+const KernelEntry *find_sub_kernel() {
+    for (const KernelEntry &k : registry())
+        if (k.sub && k.n_fft == 4096 && k.mode == spx::MODE_QUAD && k.io == SPECTRE_MIX_F32) return &k;
+    return nullptr;
+}
+
+// pre pass (radix-R stage + twiddles) -> 4096-point shared-memory kernel on R interleaved sub-transforms (in place in
+// the scratch tensor) -> post pass.  Three launches, each streaming the tensor once.
+int mix_two_pass(DeviceState &st, const KernelEntry &k, const void *v, int dtype, long long v_sb, long long v_sn, const void *gate,
+                 const void *mem, long long mem_stride, void *out, long long o_sb, long long o_sn, int B, int n_io, int n_fft,
+                 int C, int group_width, cudaStream_t stream) {
+    const int sub = 4096, R = n_fft / sub;
+    const size_t need = (size_t)B * n_fft * C * sizeof(float);
+    if (need > st.scratch_bytes) {
+        if (st.scratch) cudaFree(st.scratch);
+        st.scratch = nullptr;
+        st.scratch_bytes = 0;
+        cudaError_t e = cudaMalloc(&st.scratch, need);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(long-context scratch)");
+        st.scratch_bytes = need;
+    }
+    float *scr = reinterpret_cast<float *>(st.scratch);
+    cudaError_t e = spx::long_pass(true, R, dtype == SPECTRE_MIX_BF16, v, scr, v_sb, v_sn, B, n_io, C, sub, st.sm_count, stream);
+    if (e != cudaSuccess) return cuda_fail(e, "long-context pre pass");
+
+    const float2 *tw = nullptr;
+    if (int rc = get_twiddles(st, k, &tw)) return rc;
+    MixParams p;
+    memset(&p, 0, sizeof(p));
+    p.v = scr;
+    p.out = scr;
+    p.gate = reinterpret_cast<const float2 *>(gate);
+    p.mem = reinterpret_cast<const float2 *>(mem);
+    p.tw = tw;
+    p.v_sb = p.o_sb = (long long)sub * C;
+    p.v_sn = p.o_sn = C;
+    p.mem_stride = mem_stride;
+    p.B = B * R;
+    p.n_in = p.n_out = sub;
+    p.C = C;
+    p.group_width = group_width;
+    p.NG = C / group_width;
+    const int tile_ch = mode_channels(k.mode) * k.ncol;
+    p.tiles_per_row = (C / 4 + k.ncol - 1) / k.ncol;
+    p.num_tiles = B * R * p.tiles_per_row;
+    p.gate_tables = 2;                       // one full-length table = two half-length slots
+    p.inv_n = 1.0f / (float)n_fft;
+    p.prefetch = g_prefetch;
+    p.timeline = nullptr;
+    p.skew_ns = 0;
+    p.sub_R = R;
+    Choice c;
+    c.k = &k;
+    c.gate_tables = 2;
+    alignas(64) CUtensorMap tmap, tmap_out;
+    bool tma = g_use_tma && k.tma_ok && (int)k.smem_bytes(2, true, false) <= st.max_smem_optin &&
+               make_v_tensor_map(&tmap, scr, SPECTRE_MIX_F32, p.v_sb, p.v_sn, B * R, sub, C, spx::kTmaBoxRows, tile_ch) &&
+               make_v_tensor_map(&tmap_out, scr, SPECTRE_MIX_F32, p.o_sb, p.o_sn, B * R, sub, C, k.out_box_rows, tile_ch);
+    const bool tmem = tma && g_use_tmem && k.tmem_ok && (int)k.smem_bytes(2, true, true) <= st.max_smem_optin;
+    if (!tma && (int)k.smem_bytes(2, false, false) > st.max_smem_optin)
+        return fail(SPECTRE_MIX_ERR_UNSUPPORTED, "internal: sub-transform kernel does not fit shared memory");
+    const int occ = std::max(1, occupancy_of(st, c, mem != nullptr, tma, tmem));
+    const int grid = std::min(p.num_tiles, st.sm_count * occ);
+    e = k.launch(p, grid, mem != nullptr, tma ? &tmap : nullptr, tma ? &tmap_out : nullptr, tmem, stream);
+    if (e != cudaSuccess) return cuda_fail(e, "long-context sub-transform kernel");
+
+    e = spx::long_pass(false, R, dtype == SPECTRE_MIX_BF16, scr, out, o_sb, o_sn, B, n_io, C, sub, st.sm_count, stream);
+    if (e != cudaSuccess) return cuda_fail(e, "long-context post pass");
+    return 0;
+}
+
 }  // namespace
 
 extern "C" {
@@ -281,6 +358,11 @@ int spectre_mix_set_prefetch(int enable) {
 
 int spectre_mix_set_timeline(void *device_buffer) {
     g_timeline = reinterpret_cast<unsigned long long *>(device_buffer);
+    return 0;
+}
+
+int spectre_mix_set_two_pass(int enable) {
+    g_use_two_pass = enable ? 1 : 0;
     return 0;
 }
 
@@ -319,6 +401,12 @@ int spectre_mix_fwd(const void *v, int v_dtype, int64_t v_stride_b, int64_t v_st
 
     const int mode = pick_mode(v_dtype, group_width, v, v_stride_b, v_stride_n, out, out_stride_b, out_stride_n, mem,
                                mem_stride);
+    // long transforms: one streaming radix-R pass, R interleaved 4096-point transforms in shared memory, one streaming pass
+    if (g_use_two_pass && n_fft > 4096 && mode == spx::MODE_QUAD && group_width % 8 == 0 && (!mem || (mem_stride % 2 == 0))) {
+        if (const KernelEntry *ks = find_sub_kernel())
+            return mix_two_pass(*st, *ks, v, v_dtype, v_stride_b, v_stride_n, gate, mem, mem_stride, out, out_stride_b,
+                                out_stride_n, B, n_io, n_fft, C, group_width, reinterpret_cast<cudaStream_t>(stream));
+    }
     Choice c;
     if (int rc = choose(*st, n_fft, v_dtype, mode, C, group_width, &c)) return rc;
     const float2 *tw = nullptr;
@@ -349,6 +437,7 @@ int spectre_mix_fwd(const void *v, int v_dtype, int64_t v_stride_b, int64_t v_st
     p.prefetch = g_prefetch;
     p.timeline = g_timeline;
     p.skew_ns = g_skew_ns;
+    p.sub_R = 1;
 
     // TMA-fed variant when V's layout can be described to the TMA unit; otherwise direct 128-bit global loads
     alignas(64) CUtensorMap tmap, tmap_out;
@@ -376,8 +465,13 @@ int spectre_mix_plan(int v_dtype, int out_dtype, int has_mem, int B, int N, int 
     DeviceState *st = nullptr;
     if (int rc = get_device_state(&st, nullptr)) return rc;
     const int mode = (group_width % 4 == 0) ? spx::MODE_QUAD : ((group_width % 2 == 0) ? spx::MODE_PAIR : spx::MODE_REAL);
+    const KernelEntry *ks = (g_use_two_pass && n_fft > 4096 && mode == spx::MODE_QUAD && group_width % 8 == 0) ? find_sub_kernel() : nullptr;
     Choice c;
-    if (int rc = choose(*st, n_fft, v_dtype, mode, C, group_width, &c)) return rc;
+    if (ks) {
+        c.k = ks;
+        c.gate_tables = 2;
+        c.tiles_per_row = (C / 4 + ks->ncol - 1) / ks->ncol;
+    } else if (int rc = choose(*st, n_fft, v_dtype, mode, C, group_width, &c)) return rc;
     memset(info, 0, sizeof(*info));
     info->n_fft = n_fft;
     for (int i = 0; i < 4; ++i) info->radix[i] = c.k->radix[i];
@@ -385,8 +479,8 @@ int spectre_mix_plan(int v_dtype, int out_dtype, int has_mem, int B, int N, int 
     info->threads = c.k->threads;
     info->ctas_per_sm = std::max(1, occupancy_of(*st, c, has_mem != 0, g_use_tma && c.k->tma_ok));
     info->smem_bytes = (int)c.k->smem_bytes(c.gate_tables, g_use_tma && c.k->tma_ok, g_use_tma && g_use_tmem && c.k->tmem_ok);
-    info->grid = std::min(B * c.tiles_per_row, st->sm_count * info->ctas_per_sm);
-    info->launches = 1;
+    info->grid = std::min(B * (ks ? n_fft / 4096 : 1) * c.tiles_per_row, st->sm_count * info->ctas_per_sm);
+    info->launches = ks ? 3 : 1;   // long transforms: pre pass + 4096-point sub-transforms + post pass
     info->algorithmic_bytes = algorithmic_bytes(v_dtype, has_mem != 0, B, N, n_fft, C, group_width);
     return 0;
 }

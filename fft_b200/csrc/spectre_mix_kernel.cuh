@@ -51,6 +51,7 @@ struct MixParams {
     int gate_tables;      // gate groups a tile may touch (smem sized for this many)
     float inv_n;
     int prefetch;         // 1: prefetch the CTA's next tile into L2 while this one is transformed
+    int sub_R;            // long-context path: number of interleaved sub-transforms (n_total = sub_R * n_fft), else 1
     int skew_ns;          // experiment: delay half of the warps by this much before the warp-local passes
     unsigned long long *timeline;  // optional: per-CTA phase timestamps (ns) for tools/timeline.py, else nullptr
 };
@@ -187,8 +188,12 @@ struct Dft<16, V> {
 };
 
 // ------------------------------------------------------------------ plan (compile time)
-template <int R0, int R1, int R2, int R3>
+// SUBP: this transform is one of R interleaved sub-transforms of a longer one (n_total = R * N, first radix-R
+// stage and its twiddles done by the pre/post pass kernels of the long-context path): the input is already complex,
+// the gate is gathered with stride R and is not Hermitian within the sub-spectrum.
+template <int R0, int R1, int R2, int R3, bool SUBP = false>
 struct Plan {
+    static constexpr bool kSub = SUBP;
     static constexpr int N = R0 * R1 * R2 * R3;
     static constexpr int NS = (R3 > 1) ? 4 : ((R2 > 1) ? 3 : ((R1 > 1) ? 2 : 1));
     static_assert(NS >= 2, "at least two stages");
@@ -211,7 +216,7 @@ constexpr int kTmemSlots = 5;
 // n_fft = 8192 the (largest) stage-0 table is read through L2 instead, at 16384 every table is.
 template <class PL>
 struct TwPolicy {
-    static constexpr int FROM = (PL::N >= 16384) ? (PL::NS - 1) : ((PL::N >= 8192) ? 1 : 0);
+    static constexpr int FROM = (PL::N >= 16384) ? (PL::NS - 1) : ((PL::N >= 8192 || PL::kSub) ? 1 : 0);
     static constexpr int SMEM_N = PL::TWN - PL::TWOFF(FROM);   // entries held in shared memory
 };
 template <class PL, int S_>
@@ -587,6 +592,30 @@ __device__ __forceinline__ void cta_sync() {
     else __syncthreads();
 }
 
+// sub-transform q of a length n_total = R * N transform: bin k' of the sub-spectrum is bin k = q + R k' of the long one;
+// table[k'] = Gfull[k] / n_total with Gfull the Hermitian extension (imag of DC / Nyquist dropped)
+template <int N, int NT, int GKS>
+__device__ __forceinline__ void gate_fetch_sub(float2 (&gv)[GKS], const float2 *gp, int tid, int q, int R) {
+    const int nt = N * R;
+#pragma unroll
+    for (int j = 0; j < GKS; ++j) {
+        const int k = q + R * (tid + j * NT);
+        gv[j] = __ldg(gp + (k <= nt / 2 ? k : nt - k));
+    }
+}
+template <int N, int NT, int GKS>
+__device__ __forceinline__ void gate_put_sub(float2 *gs, const float2 (&gv)[GKS], int tid, int q, int R, float inv_n) {
+    const int nt = N * R;
+#pragma unroll
+    for (int j = 0; j < GKS; ++j) {
+        const int kp = tid + j * NT;
+        const int k = q + R * kp;
+        float im = (k <= nt / 2) ? gv[j].y : -gv[j].y;
+        if (k == 0 || k == nt / 2) im = 0.f;
+        gs[kp + (kp >> 4)] = make_float2(gv[j].x * inv_n, im * inv_n);
+    }
+}
+
 // ------------------------------------------------------------------ the kernel
 // One persistent CTA per resident slot; each loop iteration transforms one tile = all n_fft rows of NCOL
 // elements (CH channels each) of one batch row.  RFFT_ONLY: stop after the forward half and write the half
@@ -642,7 +671,10 @@ __global__ void __launch_bounds__(NT + ((TMA_IN && NT >= kSepProducerMinThreads)
     // first __syncthreads of the tile loop publishes the table
 
     constexpr int GK = (N / 2 + 1 + NT - 1) / NT;   // gate entries per thread
-    const bool gate_early = (p.gate_tables == 1);   // one table per tile: fetch the next tile's while this one finishes
+    constexpr bool SUB = PL::kSub;
+    constexpr int GKS = SUB ? N / NT : 1;           // sub-transform: full-length gate table, entries per thread
+    static_assert(!SUB || (N % NT == 0 && MODE == MODE_QUAD && !RFFT_ONLY), "sub-transform variant: packed mix kernel only");
+    const bool gate_early = SUB || (p.gate_tables == 1);   // one table per tile: fetch the next tile's while this one finishes
     const TIN *vbase = reinterpret_cast<const TIN *>(p.v);
     TOUT *obase = reinterpret_cast<TOUT *>(p.out);
     const int CE = p.C / CH;  // elements per row
@@ -859,8 +891,10 @@ __global__ void __launch_bounds__(NT + ((TMA_IN && NT >= kSepProducerMinThreads)
     };
 
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        const int b = tile / p.tiles_per_row;
-        const int ce0 = (tile - b * p.tiles_per_row) * NCOL;  // first element column of the tile
+        const int brow = tile / p.tiles_per_row;                 // row of the [B'][n_fft][C] tensor the tile lives in
+        const int b = SUB ? brow / p.sub_R : brow;               // batch row (gate / memory)
+        const int qsub = SUB ? brow % p.sub_R : 0;               // which interleaved sub-transform
+        const int ce0 = (tile - brow * p.tiles_per_row) * NCOL;  // first element column of the tile
         const int c0 = ce0 * CH;
         const int g0 = c0 / p.group_width;
         const bool full_tile = (ce0 + NCOL <= CE) && (p.n_in == N);
@@ -869,7 +903,13 @@ __global__ void __launch_bounds__(NT + ((TMA_IN && NT >= kSepProducerMinThreads)
         // ---- stage the gate tables of this tile (scaled by 1/n_fft, imag(DC)=imag(Nyquist)=0).  With one table per
         // tile this was already done while the previous tile finished (see below); else do it here.
         if constexpr (!RFFT_ONLY) {
-            if (!gate_early || tile == (int)blockIdx.x) {
+            if constexpr (SUB) {
+                if (tile == (int)blockIdx.x) {
+                    float2 gv[GKS];
+                    gate_fetch_sub<N, NT, GKS>(gv, p.gate + ((long long)b * p.NG + g0) * ((N * p.sub_R) / 2 + 1), tid, qsub, p.sub_R);
+                    gate_put_sub<N, NT, GKS>(gate_s, gv, tid, qsub, p.sub_R, p.inv_n);
+                }
+            } else if (!gate_early || tile == (int)blockIdx.x) {
                 for (int t = 0; t < p.gate_tables; ++t) {
                     const int g = g0 + t;
                     if (g < p.NG) {
@@ -917,7 +957,7 @@ __global__ void __launch_bounds__(NT + ((TMA_IN && NT >= kSepProducerMinThreads)
                 }
                 cta_sync<NT, SEP>();   // every landed element is in registers: the buffer may be rewritten in place
             } else {
-                const TIN *vb = vbase + (long long)b * p.v_sb + c0;
+                const TIN *vb = vbase + (long long)brow * p.v_sb + c0;
 #pragma unroll
                 for (int it = 0; it < ITERS0; ++it) {
                     const int w = tid + it * NT;
@@ -1007,6 +1047,22 @@ __global__ void __launch_bounds__(NT + ((TMA_IN && NT >= kSepProducerMinThreads)
                 const int nk = N - klow;                           // N - klow - PLAST q stays >= N/2 - ... >= 1
 #pragma unroll
                 for (int q = 0; q < RL; ++q) {
+                    if constexpr (SUB) {
+                        // bin k' = klow + PLAST q of this sub-spectrum = bin qsub + R k' of the long transform; the table
+                        // already holds the Hermitian-extended, conjugated-where-needed gate
+                        const int kp = klow + PLAST * q;
+                        const float2 g = gs[(PLAST % 16 == 0) ? plo + PLAST * q + ((PLAST * q) >> 4) : kp + (kp >> 4)];
+                        x[q] = cmul(x[q], g.x, g.y);
+                        if (HAS_MEM) {
+                            const int nt = N * p.sub_R, kf = qsub + p.sub_R * kp;
+                            const bool lowf = kf <= nt / 2;
+                            const int kk = lowf ? kf : nt - kf;
+                            const float sgn = (kf == 0 || kf == nt / 2) ? 0.f : (lowf ? p.inv_n : -p.inv_n);
+                            mem_add(x[q], p.mem + (long long)kk * p.mem_stride + cabs, p.inv_n, sgn, MODE);
+                        }
+                        x[q] = cswap(x[q]);
+                        continue;
+                    }
                     const bool lower = q < RL / 2;
                     int k, kp;
                     if (lower) {
@@ -1035,19 +1091,29 @@ __global__ void __launch_bounds__(NT + ((TMA_IN && NT >= kSepProducerMinThreads)
 
         // the gate table is free again: start fetching the next tile's gate row, park it in registers
         // across the inner inverse passes, and publish it before the last pass
-        float2 gnext[GK];
+        float2 gnext[SUB ? GKS : GK];
         const int tile_next = tile + gridDim.x;
         const bool fetch_next = gate_early && tile_next < p.num_tiles;
+        int nq = 0;
         if (fetch_next) {
-            const int nb = tile_next / p.tiles_per_row;
-            const int ng = ((tile_next - nb * p.tiles_per_row) * NCOL * CH) / p.group_width;
-            gate_fetch<N, NT, GK>(gnext, p.gate + ((long long)nb * p.NG + ng) * (N / 2 + 1), tid);
+            const int nrow = tile_next / p.tiles_per_row;
+            const int ng = ((tile_next - nrow * p.tiles_per_row) * NCOL * CH) / p.group_width;
+            if constexpr (SUB) {
+                nq = nrow % p.sub_R;
+                gate_fetch_sub<N, NT, GKS>(gnext, p.gate + ((long long)(nrow / p.sub_R) * p.NG + ng) * ((N * p.sub_R) / 2 + 1), tid, nq,
+                                           p.sub_R);
+            } else {
+                gate_fetch<N, NT, GK>(gnext, p.gate + ((long long)nrow * p.NG + ng) * (N / 2 + 1), tid);
+            }
         }
 
         // ---- inverse stages NS-2 .. 1: smem -> twiddle -> butterfly -> smem (in place)
         if constexpr (NS > 3) { inv_inner_pass<PL, MODE, NCOL, NT, 2>(buf, tw, p.tw, tid); cta_sync<NT, SEP>(); }
         if constexpr (NS > 2) { inv_inner_pass<PL, MODE, NCOL, NT, 1>(buf, tw, p.tw, tid); cta_sync<NT, SEP>(); }
-        if (fetch_next) gate_put<N, NT, GK>(gate_s, gnext, tid, p.inv_n);
+        if (fetch_next) {
+            if constexpr (SUB) gate_put_sub<N, NT, GKS>(gate_s, gnext, tid, nq, p.sub_R, p.inv_n);
+            else gate_put<N, NT, GK>(gate_s, gnext, tid, p.inv_n);
+        }
         SPX_MARK(5)
 
         // ---- inverse stage 0: smem -> twiddle -> butterfly -> global
@@ -1077,7 +1143,7 @@ __global__ void __launch_bounds__(NT + ((TMA_IN && NT >= kSepProducerMinThreads)
                     if (tid == 0) producer_next_load(tile, tile_it);
                 }
             }
-            TOUT *ob = obase + (long long)b * p.o_sb + c0;
+            TOUT *ob = obase + (long long)brow * p.o_sb + c0;
 #pragma unroll
             for (int it = 0; it < ITERS0; ++it) {
                 const int w = tid + it * NT;

@@ -25,6 +25,7 @@ struct KernelEntry {
     int (*occupancy)(int gate_tables, bool has_mem, bool tma, bool tmem);
     int tma_ok;    // 1: a TMA-fed variant exists (packed mode, landed row >= 16 bytes)
     int tmem_ok;   // 1: a TMEM-staged variant exists (tile I/O parked in tensor memory by a helper warpgroup)
+    int sub;       // 1: sub-transform variant of the long-context two-pass path (complex input, strided gate gather)
     // forward half only (half spectrum out); MODE_REAL variants only, else nullptr
     cudaError_t (*launch_rfft)(const MixParams &p, int grid, cudaStream_t st);
 };
@@ -112,8 +113,21 @@ struct RfftPtr<PL, MODE_REAL, NCOL, NT, MINB, TIO> {
             &::spx::Launcher<::spx::Plan<R0, R1, R2, R3>, MODE, NCOL, NT, MINB, TIO>::launch,                 \
             &::spx::Launcher<::spx::Plan<R0, R1, R2, R3>, MODE, NCOL, NT, MINB, TIO>::occupancy,              \
             ::spx::Launcher<::spx::Plan<R0, R1, R2, R3>, MODE, NCOL, NT, MINB, TIO>::kTma ? 1 : 0,            \
-            ::spx::Launcher<::spx::Plan<R0, R1, R2, R3>, MODE, NCOL, NT, MINB, TIO>::kTmem ? 1 : 0,           \
+            ::spx::Launcher<::spx::Plan<R0, R1, R2, R3>, MODE, NCOL, NT, MINB, TIO>::kTmem ? 1 : 0, 0,        \
             ::spx::RfftPtr<::spx::Plan<R0, R1, R2, R3>, MODE, NCOL, NT, MINB, TIO>::get()                     \
+    }
+
+#define SPX_ENTRY_SUB(R0, R1, R2, R3, MODE, NCOL, NT, MINB, TIO, IOCODE)                                     \
+    {                                                                                                         \
+        (R0) * (R1) * (R2) * (R3), {R0, R1, R2, R3}, MODE, IOCODE, NCOL, NT, MINB,                            \
+            ::spx::Plan<R0, R1, R2, R3, true>::TWN,                                                           \
+            &::spx::Launcher<::spx::Plan<R0, R1, R2, R3, true>, MODE, NCOL, NT, MINB, TIO>::smem_bytes,       \
+            ::spx::Smem<::spx::Plan<R0, R1, R2, R3, true>, MODE, NCOL>::OUT_BOX_ROWS,                         \
+            &::spx::Launcher<::spx::Plan<R0, R1, R2, R3, true>, MODE, NCOL, NT, MINB, TIO>::launch,           \
+            &::spx::Launcher<::spx::Plan<R0, R1, R2, R3, true>, MODE, NCOL, NT, MINB, TIO>::occupancy,        \
+            ::spx::Launcher<::spx::Plan<R0, R1, R2, R3, true>, MODE, NCOL, NT, MINB, TIO>::kTma ? 1 : 0,      \
+            ::spx::Launcher<::spx::Plan<R0, R1, R2, R3, true>, MODE, NCOL, NT, MINB, TIO>::kTmem ? 1 : 0, 1,  \
+            nullptr                                                                                           \
     }
 
 // one table per instantiation file

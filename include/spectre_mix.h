@@ -124,6 +124,9 @@ int spectre_mix_set_tma(int enable);
  * exists (n_fft = 4096 fp32).  For experiments only. */
 int spectre_mix_set_tmem(int enable);
 
+/* Enable (default) / disable the two-pass path for n_fft > 4096 (falls back to the single-kernel variants). */
+int spectre_mix_set_two_pass(int enable);
+
 /* Experiment: hold back half of the warps by `ns` nanoseconds before the warp-local passes (0 = off). */
 int spectre_mix_set_skew_ns(int ns);
 

@@ -358,3 +358,61 @@ def test_decode_split_equals_fused(fb, dev):
         b = c2.fused_step(v, v_old, gate)
         assert torch.allclose(a, b, rtol=1e-5, atol=1e-5)
     assert torch.equal(c1.prefix_fft, c2.prefix_fft)
+
+
+# --------------------------------------------------------------------------- BASELINE config 3: full model, bf16
+def test_spectre_base_bf16_forward(fb, dev):
+    """12 blocks, d=768, 12 heads, seq=4096 under bf16 autocast: runs through the bf16 kernel variant and stays close
+    to the same model evaluated in fp32 (the stock reference cannot run in bf16 on CUDA at all)."""
+    torch.manual_seed(40)
+    model = fb.SpectreBase(vocab=1000, depth=12).to(dev).eval()
+    tokens = torch.randint(0, 1000, (1, 4096), device=dev)
+    with torch.no_grad():
+        h32 = model(tokens, return_hidden=True)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            h16 = model(tokens, return_hidden=True)
+    assert h32.shape == (1, 4096, 768) and torch.isfinite(h16).all()
+    err = (h16.float() - h32).norm() / h32.norm()
+    assert err < 5e-2, err
+
+
+def test_patch_reference_style_module(fb, dev):
+    """patch_reference() rebinds forward on modules matched by class name; emulate a reference-built module tree."""
+    import types
+    torch.manual_seed(41)
+    blk = fb.SpectreBlock(64, 4, 128, pooling_type="mean", wavelet_on_rate=0.0).to(dev).eval()
+    x = torch.randn(2, 128, 64, device=dev)
+    with torch.no_grad():
+        y0 = blk(x)
+    blk.mix.forward = types.MethodType(lambda self, *a, **k: (_ for _ in ()).throw(RuntimeError("stock forward")), blk.mix)
+    assert fb.patch_reference(blk) >= 1
+    with torch.no_grad():
+        y1 = blk(x)
+    assert torch.equal(y0, y1)
+
+
+def test_long_context_two_pass_and_single_kernel_agree(fb, oracle, dev):
+    """n_fft = 8192 / 16384: the two-pass path (radix-R streaming pass + 4096-point sub-transforms + streaming pass) and
+    the single-kernel variants both match the oracle; ragged N, memory, bf16 included."""
+    from fft_b200 import _lib
+    lib = _lib.load()
+    cases = [(2, 8192, 8192, 32, 16, True), (1, 16384, 16384, 48, 8, True), (2, 12000, 16384, 16, 16, False),
+             (1, 20000, 16384, 16, 16, False)]
+    for (B, N, n_fft, C, dg, with_mem) in cases:
+        V, gate, mem = _rand_case(B, N, n_fft, C, dg, with_mem, seed=50 + N)
+        want = oracle.mix_flat(V, gate, n_fft, dg, mem).numpy()
+        args = (V.to(dev), gate.to(dev), None if mem is None else mem.to(dev))
+        try:
+            lib.spectre_mix_set_two_pass(1)
+            y2 = fb.spectral_mix(*args, n_fft=n_fft, group_width=dg)
+            lib.spectre_mix_set_two_pass(0)
+            y1 = fb.spectral_mix(*args, n_fft=n_fft, group_width=dg)
+        finally:
+            lib.spectre_mix_set_two_pass(1)
+        _check(y2, want)
+        _check(y1, want)
+    assert fb.plan_info(4, 16384, 16384, 768, 16)["launches"] == 3
+    Vb = torch.randn(1, 16384, 32, generator=torch.Generator().manual_seed(60)).to(torch.bfloat16)
+    gate = torch.randn(1, 2, 8193, dtype=torch.cfloat, generator=torch.Generator().manual_seed(61))
+    y = fb.spectral_mix(Vb.to(dev), gate.to(dev), n_fft=16384, group_width=16)
+    _check(y, oracle.mix_flat(Vb.float(), gate, 16384, 16).numpy(), rl2=REL_L2_BF16, mabs=2e-2)
