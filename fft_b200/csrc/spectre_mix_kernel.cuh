@@ -667,8 +667,13 @@ __global__ void __launch_bounds__(NT + ((TMA_IN && NT >= kSepProducerMinThreads)
     constexpr int CPR = NCOL * 4;                        // TMEM columns per tile row (fp32 channels)
     constexpr int TCOLS = PL::N / 128 * CPR;             // TMEM columns of one parked tile (256 at 4096 x 8 ch)
     const int tid = threadIdx.x;
-    for (int i = tid; i < TwPolicy<PL>::SMEM_N; i += NT) tw[i] = p.tw[PL::TWOFF(TwPolicy<PL>::FROM) + i];
-    // first __syncthreads of the tile loop publishes the table
+    // twiddle tables -> shared memory, once per (persistent) CTA: one bulk-async copy (TMA, UBLKCP) in the TMA variants,
+    // plain loads otherwise; the first barrier of the tile loop publishes the table
+    constexpr uint32_t TW_BYTES = (uint32_t)(sizeof(float2) * TwPolicy<PL>::SMEM_N);
+    constexpr bool TW_BULK = TMA_IN && (TW_BYTES % 16 == 0) && TW_BYTES > 0;
+    if constexpr (!TW_BULK) {
+        for (int i = tid; i < TwPolicy<PL>::SMEM_N; i += NT) tw[i] = p.tw[PL::TWOFF(TwPolicy<PL>::FROM) + i];
+    }
 
     constexpr int GK = (N / 2 + 1 + NT - 1) / NT;   // gate entries per thread
     constexpr bool SUB = PL::kSub;
@@ -720,6 +725,17 @@ __global__ void __launch_bounds__(NT + ((TMA_IN && NT >= kSepProducerMinThreads)
         if (rnd_p >= 1) mbar_arrive(bar_stg_free + 8 * (kbuf ^ 1));
         ++rnd_p;
     };
+    if constexpr (TW_BULK) {
+        const uint32_t bar_tw = bar + 104;
+        if (tid == 0) {
+            mbar_init(bar_tw, 1);
+            mbar_expect_tx(bar_tw, TW_BYTES);
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(tw)),
+                         "l"(p.tw + PL::TWOFF(TwPolicy<PL>::FROM)), "r"(TW_BYTES), "r"(bar_tw)
+                         : "memory");
+            mbar_wait(bar_tw, 0);   // the set-up barrier below (all threads) orders this before any use
+        }
+    }
     // ---------------------------------------------------------------- TMEM-staged variant: set-up + helper warpgroup
     // barriers:  +0 tile parked in TMEM-IN (helper)   +8 TMEM-IN consumed (NW warps)   +16 results parked in TMEM-OUT (NW warps)
     //            +24 TMEM-OUT drained (helper)   +32.. ring slot landed (TMA tx, kTmemSlots of them)   +96 TMEM base address
