@@ -165,14 +165,9 @@ class WaveletRefinement(nn.Module):
 
 
 # ----------------------------------------------------------------------------- forward logic (shared with patch_reference)
-def head_project_and_gate(head, x: torch.Tensor, pos_phase: Optional[torch.Tensor]):
-    """Everything of SpectreHead.forward that is NOT the hot path: spectre.py:502-503 and :511-536.
-
-    Works on our shells and on the reference's own ``SpectreHead`` (same attribute names).
-    Returns V (B, N, d_h), gate_half (B, G, F_half) complex64, q_pool (B, d_h).
-    """
-    Q = head.W_q(x)
-    V = head.W_v(x)
+def head_gate(head, Q: torch.Tensor, pos_phase: Optional[torch.Tensor]):
+    """Gate generator of one head, spectre.py:511-536: pooled descriptor -> anchors -> cubic interpolation -> modReLU
+    (-> positional phase).  Returns gate_half (B, G, F_half) complex64 and q_pool (B, d_h)."""
     q_pool = head.q_norm(head.pooling(Q))
     Bsz = q_pool.shape[0]
     anchors = head.gate_mlp(q_pool).float().view(Bsz, head.G, head.B, 2)
@@ -183,6 +178,18 @@ def head_project_and_gate(head, x: torch.Tensor, pos_phase: Optional[torch.Tenso
     gate_half = head.modrelu(gate_half.reshape(Bsz, -1)).view_as(gate_half)
     if pos_phase is not None:
         gate_half = gate_half * pos_phase.unsqueeze(1 if pos_phase.dim() == 2 else 0)
+    return gate_half, q_pool
+
+
+def head_project_and_gate(head, x: torch.Tensor, pos_phase: Optional[torch.Tensor]):
+    """Everything of SpectreHead.forward that is NOT the hot path: spectre.py:502-503 and :511-536.
+
+    Works on our shells and on the reference's own ``SpectreHead`` (same attribute names).
+    Returns V (B, N, d_h), gate_half (B, G, F_half) complex64, q_pool (B, d_h).
+    """
+    Q = head.W_q(x)
+    V = head.W_v(x)
+    gate_half, q_pool = head_gate(head, Q, pos_phase)
     return V, gate_half, q_pool
 
 
@@ -195,21 +202,34 @@ def head_forward(head, x, pos_phase=None, return_q_pool=False, memory_fft=None):
     return (result, q_pool) if return_q_pool else result
 
 
+def _stacked(mods, name):
+    """(H, out, in) stack of the per-head Linear weights `name` (kept as separate parameters for state_dict parity)."""
+    return torch.stack([getattr(h, name).weight for h in mods], dim=0)
+
+
 def multihead_forward(mh, x, pos_phase=None, memory_fft=None):
-    """``SpectreMultiHead.forward`` (spectre.py:701-726): all heads in ONE kernel launch."""
-    chunks = torch.chunk(x, mh.num_heads, dim=-1)
-    Vs, gates, pools = [], [], []
-    for h, c in zip(mh.heads, chunks):
-        V, g, qp = head_project_and_gate(h, c, pos_phase)
-        Vs.append(V)
+    """``SpectreMultiHead.forward`` (spectre.py:701-726): all heads in ONE kernel launch.
+
+    The per-head projections of spectre.py:502-503 are evaluated as one batched GEMM over the stacked head weights
+     -- same arithmetic per head, no chunk / cat copies; the gate generator runs per head on the pooled
+    descriptor exactly as the reference does.
+    """
+    H = mh.num_heads
+    h0 = mh.heads[0]
+    B, N, d = x.shape
+    xh = x.view(B, N, H, d // H)
+    W_v, W_q = _stacked(mh.heads, "W_v"), _stacked(mh.heads, "W_q")
+    V_all = torch.einsum("bnhi,hoi->bnho", xh, W_v).reshape(B, N, d)     # head h = channels [h*d_h, (h+1)*d_h)
+    Q_all = torch.einsum("bnhi,hoi->bnho", xh, W_q)                      # (B, N, H, d_h)
+    gates, pools = [], []
+    for i, h in enumerate(mh.heads):
+        g, qp = head_gate(h, Q_all[:, :, i, :], pos_phase)
         gates.append(g)
         pools.append(qp)
-    h0 = mh.heads[0]
-    V_all = torch.cat(Vs, dim=-1)              # (B, N, d): head h = channels [h*d_h, (h+1)*d_h)
     gate_all = torch.cat(gates, dim=1)         # (B, H*G, F_half)
     mixed = spectral_mix(V_all, gate_all, memory_fft, n_fft=h0.n_fft, group_width=h0.d_g)
     if not isinstance(h0.dropout, nn.Identity):  # per-head dropout modules, applied on their slices (:553)
-        mixed = torch.cat([h.dropout(m) for h, m in zip(mh.heads, torch.chunk(mixed, mh.num_heads, dim=-1))], dim=-1)
+        mixed = torch.cat([h.dropout(m) for h, m in zip(mh.heads, torch.chunk(mixed, H, dim=-1))], dim=-1)
     q_pool = torch.cat(pools, dim=-1)
     return mh.out_proj(mh.wavelet_refinement(mixed, q_pool))
 

@@ -416,3 +416,26 @@ def test_long_context_two_pass_and_single_kernel_agree(fb, oracle, dev):
     gate = torch.randn(1, 2, 8193, dtype=torch.cfloat, generator=torch.Generator().manual_seed(61))
     y = fb.spectral_mix(Vb.to(dev), gate.to(dev), n_fft=16384, group_width=16)
     _check(y, oracle.mix_flat(Vb.float(), gate, 16384, 16).numpy(), rl2=REL_L2_BF16, mabs=2e-2)
+
+
+def test_randomised_shapes(fb, oracle, dev):
+    """Seeded random walk over the argument space: every supported n_fft, ragged N (both sides of n_fft), channel
+    counts that leave partial tiles, group widths of every element mode, memory on/off, row-strided views."""
+    rng = np.random.default_rng(1234)
+    for trial in range(60):
+        n_fft = int(2 ** rng.integers(5, 13))                     # 32 .. 4096
+        N = int(rng.integers(1, int(n_fft * 1.3) + 2))
+        dg = int(rng.choice([1, 2, 3, 4, 6, 8, 12, 16]))
+        C = dg * int(rng.integers(1, 7))
+        B = int(rng.integers(1, 4))
+        with_mem = bool(rng.integers(0, 2))
+        V, gate, mem = _rand_case(B, N, n_fft, C, dg, with_mem, seed=1000 + trial)
+        want = oracle.mix_flat(V, gate, n_fft, dg, mem).numpy()
+        Vd = V.to(dev)
+        if trial % 3 == 0:                                         # a view with a row stride larger than C
+            wide = torch.zeros(B, N, C + 8, device=dev)
+            wide[:, :, 4:4 + C] = Vd
+            Vd = wide[:, :, 4:4 + C]
+        got = fb.spectral_mix(Vd, gate.to(dev), None if mem is None else mem.to(dev), n_fft=n_fft, group_width=dg)
+        e1, e2 = rel_l2(got.cpu().numpy(), want), max_abs_rel(got.cpu().numpy(), want)
+        assert e1 <= REL_L2_F32 and e2 <= MAX_ABS_F32, (trial, B, N, n_fft, C, dg, with_mem, e1, e2)
