@@ -25,6 +25,7 @@ SYMBOLS = (
     "spectre_decode_update",
     "spectre_decode_readout",
     "spectre_decode_step",
+    "spectre_gate_expand",
     "spectre_mix_plan",
     "spectre_mix_set_tile_channels",
     "spectre_mix_set_prefetch",
@@ -86,6 +87,8 @@ def load():
         lib.spectre_decode_readout.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp]
         lib.spectre_decode_step.restype = i32
         lib.spectre_decode_step.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, ctypes.c_longlong, vp]
+        lib.spectre_gate_expand.restype = i32
+        lib.spectre_gate_expand.argtypes = [vp, vp, vp, vp, ctypes.c_longlong, vp, i32, i32, i32, i32, i32, vp]
         lib.spectre_mix_plan.restype = i32
         lib.spectre_mix_plan.argtypes = [i32, i32, i32, i32, i32, i32, i32, i32, ctypes.POINTER(PlanInfo)]
         lib.spectre_mix_set_tile_channels.restype = i32

@@ -12,6 +12,7 @@ runs ``rfft -> gate * V_fft (+ memory) -> irfft -> [:N]`` once per head (:506, :
 from __future__ import annotations
 
 import math
+import sys
 import types
 import warnings
 from typing import Optional
@@ -20,7 +21,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from .ops import spectral_mix
+from .ops import gate_expand, spectral_mix
 
 try:  # optional, like the reference (spectre.py:10-14)
     import torch_dct as _dct
@@ -155,6 +156,8 @@ class WaveletRefinement(nn.Module):
 
     def forward(self, v: torch.Tensor, q_pool: torch.Tensor) -> torch.Tensor:
         B = v.shape[0]
+        if self.on_rate <= 0.0:
+            return v          # rand() < 0 never fires: skip the mask and the host sync of `on.any()` below
         on = torch.rand(B, 1, 1, device=v.device) < self.on_rate
         if not on.any():
             return v
@@ -174,6 +177,11 @@ def head_gate(head, Q: torch.Tensor, pos_phase: Optional[torch.Tensor]):
     gate_anchor = torch.view_as_complex(anchors.contiguous())
     if head.use_toeplitz:
         raise NotImplementedError("use_toeplitz=True is not constructible in the reference (spectre.py:457)")
+    if gate_anchor.is_cuda:
+        # interpolation + modReLU + positional phase (spectre.py:526-536) in one launch
+        gate_half = gate_expand(gate_anchor, head.modrelu.bias.view(head.G, head.F_half),
+                                head.modrelu.eps.reshape(1).expand(head.G), pos_phase, F_half=head.F_half, G=head.G)
+        return gate_half, q_pool
     gate_half = interp_complex_1d(gate_anchor, size=head.F_half, mode="cubic")
     gate_half = head.modrelu(gate_half.reshape(Bsz, -1)).view_as(gate_half)
     if pos_phase is not None:
@@ -202,35 +210,96 @@ def head_forward(head, x, pos_phase=None, return_q_pool=False, memory_fft=None):
     return (result, q_pool) if return_q_pool else result
 
 
-def _stacked(mods, name):
-    """(H, out, in) stack of the per-head Linear weights `name` (kept as separate parameters for state_dict parity)."""
-    return torch.stack([getattr(h, name).weight for h in mods], dim=0)
+def _stacked(mh, path: str) -> torch.Tensor:
+    """Per-head parameter `path` (e.g. ``"gate_mlp.0.weight"``) of every head stacked along a new leading axis.
+
+    The heads keep their own parameters (state_dict parity with spectre.py:677-690); the stack is rebuilt when
+    gradients are needed and cached on the module (keyed by storage and version counters) otherwise.
+    """
+    ps = [h.get_parameter(path) if path.rsplit(".", 1)[-1] != "eps" else h.get_buffer(path) for h in mh.heads]
+    if torch.is_grad_enabled() and any(p.requires_grad for p in ps):
+        return torch.stack(ps, dim=0)
+    cache = mh.__dict__.setdefault("_spx_stacks", {})
+    key = tuple((p.data_ptr(), p._version) for p in ps)
+    hit = cache.get(path)
+    if hit is None or hit[0] != key:
+        with torch.no_grad():
+            hit = (key, torch.stack([p.detach() for p in ps], dim=0))
+        cache[path] = hit
+    return hit[1]
+
+
+def _mean_like(pooling) -> bool:
+    """Pooling modules that reduce to ``x.mean(dim=1)``: MeanPool, and DCTPooling without torch_dct (spectre.py:150-155)."""
+    name = type(pooling).__name__
+    if name == "MeanPool":
+        return True
+    if name == "DCTPooling":
+        mod = sys.modules.get(type(pooling).__module__)
+        have = getattr(mod, "_HAVE_DCT", None)
+        return (not have) if have is not None else (_dct is None)
+    return False
+
+
+def _heads_batchable(mh) -> bool:
+    h0 = mh.heads[0]
+    return all(_mean_like(h.pooling) and not h.use_toeplitz and (h.G, h.B, h.F_half, h.d) == (h0.G, h0.B, h0.F_half, h0.d)
+               and len(h.gate_mlp) == 3 and h.q_norm.eps == h0.q_norm.eps for h in mh.heads)
+
+
+def multihead_gate(mh, Q_all: torch.Tensor, pos_phase: Optional[torch.Tensor]):
+    """Gate generator of ALL heads at once (spectre.py:511-536 evaluated H times by the loop of :712-713).
+
+    Q_all (B, N, H, d_h).  Pooled descriptor -> per-head LayerNorm -> per-head 2-layer MLP as two batched GEMMs over the
+    stacked head weights -> anchors (B, H*G, Bk) -> ONE ``gate_expand`` launch (cubic interpolation, modReLU, phase).
+    Returns gate (B, H*G, F_half) complex64 and q_pool (B, H*d_h), the concatenation of :718-719.
+    """
+    heads, h0 = mh.heads, mh.heads[0]
+    H, G, Bk, F_half = len(heads), h0.G, h0.B, h0.F_half
+    Bsz = Q_all.shape[0]
+    if any(type(h.pooling).__name__ == "DCTPooling" for h in heads):
+        warnings.warn("DCT pooling unavailable, falling back to mean pooling. "
+                      "Consider installing torch_dct or re-tuning hyperparameters.")
+    q_pool = Q_all.mean(dim=1)                                                            # (B, H, d_h)   :511 pooling
+    qn = F.layer_norm(q_pool, (h0.d,), None, None, h0.q_norm.eps)
+    qn = qn * _stacked(mh, "q_norm.weight") + _stacked(mh, "q_norm.bias")                 # :511 q_norm
+    hid = torch.einsum("bhi,hoi->bho", qn, _stacked(mh, "gate_mlp.0.weight")) + _stacked(mh, "gate_mlp.0.bias")
+    hid = h0.gate_mlp[1](hid)
+    anc = torch.einsum("bhi,hoi->bho", hid, _stacked(mh, "gate_mlp.2.weight")) + _stacked(mh, "gate_mlp.2.bias")   # :515
+    anchors = torch.view_as_complex(anc.float().reshape(Bsz, H * G, Bk, 2).contiguous())  # :516
+    bias = _stacked(mh, "modrelu.bias").reshape(H * G, F_half)
+    eps = _stacked(mh, "modrelu.eps").reshape(H).repeat_interleave(G)
+    gate = gate_expand(anchors, bias, eps, pos_phase, F_half=F_half, G=G)                    # :526-536
+    return gate, qn.reshape(Bsz, H * h0.d)
 
 
 def multihead_forward(mh, x, pos_phase=None, memory_fft=None):
     """``SpectreMultiHead.forward`` (spectre.py:701-726): all heads in ONE kernel launch.
 
     The per-head projections of spectre.py:502-503 are evaluated as one batched GEMM over the stacked head weights
-     -- same arithmetic per head, no chunk / cat copies; the gate generator runs per head on the pooled
-    descriptor exactly as the reference does.
+     -- same arithmetic per head, no chunk / cat copies -- and the gate generators of all heads as one
+    batched pass ending in the fused gate-expansion kernel; heads with a pooling that is not a plain
+    mean (attention, DCT with torch_dct) fall back to the per-head generator.
     """
     H = mh.num_heads
     h0 = mh.heads[0]
     B, N, d = x.shape
     xh = x.view(B, N, H, d // H)
-    W_v, W_q = _stacked(mh.heads, "W_v"), _stacked(mh.heads, "W_q")
-    V_all = torch.einsum("bnhi,hoi->bnho", xh, W_v).reshape(B, N, d)     # head h = channels [h*d_h, (h+1)*d_h)
-    Q_all = torch.einsum("bnhi,hoi->bnho", xh, W_q)                      # (B, N, H, d_h)
-    gates, pools = [], []
-    for i, h in enumerate(mh.heads):
-        g, qp = head_gate(h, Q_all[:, :, i, :], pos_phase)
-        gates.append(g)
-        pools.append(qp)
-    gate_all = torch.cat(gates, dim=1)         # (B, H*G, F_half)
+    V_all = torch.einsum("bnhi,hoi->bnho", xh, _stacked(mh, "W_v.weight")).reshape(B, N, d)   # head h = channels [h*d_h, (h+1)*d_h)
+    Q_all = torch.einsum("bnhi,hoi->bnho", xh, _stacked(mh, "W_q.weight"))                    # (B, N, H, d_h)
+    if x.is_cuda and _heads_batchable(mh):
+        gate_all, q_pool = multihead_gate(mh, Q_all, pos_phase)
+    else:
+        gates, pools = [], []
+        for i, h in enumerate(mh.heads):
+            g, qp = head_gate(h, Q_all[:, :, i, :], pos_phase)
+            gates.append(g)
+            pools.append(qp)
+        gate_all = torch.cat(gates, dim=1)         # (B, H*G, F_half)
+        q_pool = torch.cat(pools, dim=-1)
     mixed = spectral_mix(V_all, gate_all, memory_fft, n_fft=h0.n_fft, group_width=h0.d_g)
     if not isinstance(h0.dropout, nn.Identity):  # per-head dropout modules, applied on their slices (:553)
         mixed = torch.cat([h.dropout(m) for h, m in zip(mh.heads, torch.chunk(mixed, H, dim=-1))], dim=-1)
-    q_pool = torch.cat(pools, dim=-1)
     return mh.out_proj(mh.wavelet_refinement(mixed, q_pool))
 
 

@@ -177,6 +177,94 @@ def rfft_seq(V: torch.Tensor, n_fft: int) -> torch.Tensor:
     return spec[0] if squeeze else spec
 
 
+# ----------------------------------------------------------------------------- gate generator tail
+def _gate_expand_impl(anchors: torch.Tensor, bias: torch.Tensor, eps: torch.Tensor, pos_phase: Optional[torch.Tensor],
+                      F_half: int, G: int) -> torch.Tensor:
+    _require_cuda(anchors, "anchors")
+    if anchors.dim() != 3 or not anchors.is_complex():
+        raise ValueError(f"anchors must be complex (B, NG, Bk), got {tuple(anchors.shape)} {anchors.dtype}")
+    B, NG, Bk = anchors.shape
+    if G <= 0 or NG % G:
+        raise ValueError(f"NG={NG} is not a multiple of the gate rows per head G={G}")
+    if tuple(bias.shape) != (NG, F_half):
+        raise ValueError(f"bias must be (NG, F_half) = {(NG, F_half)}, got {tuple(bias.shape)}")
+    if tuple(eps.shape) != (NG,):
+        raise ValueError(f"eps must be (NG,) = {(NG,)}, got {tuple(eps.shape)}")
+    anchors = anchors.to(torch.complex64).contiguous()
+    bias = bias.to(device=anchors.device, dtype=torch.float32).contiguous()
+    eps = eps.to(device=anchors.device, dtype=torch.float32).contiguous()
+    pos_ptr, pos_stride = None, 0
+    if pos_phase is not None:
+        pos_phase = pos_phase.to(device=anchors.device, dtype=torch.complex64)
+        if pos_phase.dim() == 1:
+            pos_phase = pos_phase.unsqueeze(0)
+        if pos_phase.dim() != 2 or pos_phase.shape[-1] != F_half or pos_phase.shape[0] not in (1, B):
+            raise ValueError(f"pos_phase must be (F_half,), (1, F_half) or (B, F_half), got {tuple(pos_phase.shape)}")
+        pos_phase = pos_phase.contiguous()
+        pos_ptr, pos_stride = pos_phase.data_ptr(), (F_half if pos_phase.shape[0] == B and B > 1 else 0)
+    gate = torch.empty((B, NG, F_half), dtype=torch.complex64, device=anchors.device)
+    if gate.numel():
+        lib = _lib.load()
+        with torch.cuda.device(anchors.device):
+            stream = torch.cuda.current_stream(anchors.device).cuda_stream
+            rc = lib.spectre_gate_expand(anchors.data_ptr(), bias.data_ptr(), eps.data_ptr(), pos_ptr, pos_stride,
+                                         gate.data_ptr(), B, NG, G, Bk, F_half, ctypes.c_void_p(stream))
+        _lib.check(rc, "gate_expand")
+    return gate
+
+
+def _gate_expand_torch(anchors, bias, eps, pos_phase, F_half, G):
+    """The same function in stock PyTorch ops (spectre.py:526-536); used to differentiate the fused kernel."""
+    from .modules import interp_complex_1d
+    B, NG, Bk = anchors.shape
+    # per head, as the reference calls it (the real/imag row shuffle of spectre.py:41 stays inside a head)
+    g = interp_complex_1d(anchors.reshape(B * (NG // G), G, Bk), size=F_half, mode="cubic").reshape(B, NG, F_half)
+    mag = torch.abs(g)
+    scale = torch.relu(mag + bias) / torch.sqrt(mag.square() + eps[:, None].square())
+    g = g * scale
+    if pos_phase is not None:
+        g = g * (pos_phase.unsqueeze(1) if pos_phase.dim() == 2 else pos_phase)
+    return g
+
+
+class _GateExpand(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, anchors, bias, eps, pos_phase, F_half, G):
+        ctx.F_half, ctx.G = F_half, G
+        ctx.save_for_backward(anchors, bias, eps, pos_phase)
+        return _gate_expand_impl(anchors, bias, eps, pos_phase, F_half, G)
+
+    @staticmethod
+    def backward(ctx, dgate):
+        anchors, bias, eps, pos_phase = ctx.saved_tensors
+        with torch.enable_grad():
+            a = anchors.detach().requires_grad_(ctx.needs_input_grad[0])
+            b = bias.detach().requires_grad_(ctx.needs_input_grad[1])
+            g = _gate_expand_torch(a, b, eps, pos_phase, ctx.F_half, ctx.G)
+            wanted = [t for t, need in ((a, ctx.needs_input_grad[0]), (b, ctx.needs_input_grad[1])) if need]
+            grads = list(torch.autograd.grad(g, wanted, dgate)) if wanted else []
+        da = grads.pop(0) if ctx.needs_input_grad[0] else None
+        db = grads.pop(0) if ctx.needs_input_grad[1] else None
+        return da, db, None, None, None, None
+
+
+def gate_expand(anchors: torch.Tensor, bias: torch.Tensor, eps: torch.Tensor, pos_phase: Optional[torch.Tensor] = None,
+                *, F_half: int, G: int) -> torch.Tensor:
+    """Gate generator tail for ALL heads in one launch: cubic interpolation of the anchors to ``F_half`` bins,
+    modReLU, optional positional phase (``spectre.py:526-536``, ``:26-61``, ``:109-121``).
+
+    anchors   (B, NG, Bk) complex64 -- ``gate_mlp`` output viewed as complex, heads stacked along NG
+    bias      (NG, F_half) float32  -- ``modrelu.bias`` of every head, stacked
+    eps       (NG,) float32         -- ``modrelu.eps`` of the head each row belongs to
+    pos_phase optional complex (F_half,), (1, F_half) or (B, F_half)
+    G         gate rows per head: the reference interpolates each head's (G, Bk) block through a reshape that pairs
+              consecutive rows of [re_0..re_{G-1}, im_0..im_{G-1}] as (real, imag) planes (spectre.py:41); kept as is
+    returns   (B, NG, F_half) complex64.  Differentiable w.r.t. anchors and bias (backward in stock PyTorch ops).
+    """
+    _require_cuda(anchors, "anchors")
+    return _GateExpand.apply(anchors, bias, eps, pos_phase, int(F_half), int(G))
+
+
 def spectral_mix_host(V: torch.Tensor, gate: torch.Tensor, memory: Optional[torch.Tensor] = None, *,
                       n_fft: int, group_width: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Same function on HOST tensors through ``spectre_mix_fwd_host`` (copies inside the call).

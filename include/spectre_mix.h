@@ -95,6 +95,21 @@ int spectre_decode_readout(const void *prefix_fft, const void *gate, float *out,
 int spectre_decode_step(void *prefix_fft, const float *v_new, const float *v_old, const void *gate, float *out, int n_fft,
                         int d, int group_width, long long t, void *stream);
 
+/* ---- gate generator tail: for ALL heads of a layer in one launch,
+ *   gate[b, g, k] = modReLU_g( cubic_interp(planes of anchors[b, head(g)])(k) ) * pos_phase[b or 0, k]
+ * where, as in the reference (spectre.py:41 reshapes a (B, 2, G, K) stack to (B*G, 2, 1, K)), the real / imaginary
+ * planes of gate row j of a head are rows 2j and 2j+1 of the list [re_0 .. re_{G-1}, im_0 .. im_{G-1}] of that head's
+ * anchor rows; G = gate rows per head (NG = heads * G).
+ * Replaces, per head, interp_complex_1d(..., mode="cubic") spectre.py:526-528 (-> :26-61: grid_sample bicubic, border,
+ * align_corners=True), ComplexModReLU spectre.py:531 (-> :109-121) and the positional phase spectre.py:534-536.
+ *   anchors    device, complex64 [B][NG][Bk]   (gate_mlp output viewed as complex, spectre.py:515-516, heads stacked)
+ *   bias       device, float32 [NG][F_half]    (modrelu.bias of every head, stacked)
+ *   eps        device, float32 [NG]            (modrelu.eps of the head each gate row belongs to)
+ *   pos_phase  device or NULL, complex64 [*][F_half]; pos_stride_b = F_half for a per-sample phase, 0 for a shared one
+ *   gate       device, complex64 [B][NG][F_half] */
+int spectre_gate_expand(const void *anchors, const float *bias, const float *eps, const void *pos_phase,
+                        long long pos_stride_b, void *gate, int B, int NG, int G, int Bk, int F_half, void *stream);
+
 /* Tuning / introspection used by bench.py and the tests (not needed by a binding). */
 typedef struct spectre_mix_plan_info {
     int n_fft;

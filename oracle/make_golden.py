@@ -17,6 +17,7 @@ test.  The GPU box has no /root/reference, so the vectors are committed.
 """
 from __future__ import annotations
 
+import math
 import os
 import sys
 
@@ -173,6 +174,29 @@ def main():
              prefix_fft=cache.prefix_fft.numpy(), sum_q=cache.sum_q.numpy(), t=np.int64(cache.t))
     np.savez_compressed(os.path.join(OUT, "decode_seq_n256_d32.npz"), **d)
     print("decode_seq_n256_d32 written", outs.shape)
+
+    # (10) gate generator tail: the reference's own interp_complex_1d (spectre.py:26-61) and ComplexModReLU
+    # (:109-121) on random anchors, with a bias spread that exercises the ReLU cut-off, and the positional phase of :534-536
+    for name, seed, n_fft, G, Bsz in (("gate_n128_g4", 30, 128, 4, 3), ("gate_n4096_g4", 31, 4096, 4, 2),
+                                      ("gate_n1000_g3", 32, 1000, 3, 2)):
+        torch.manual_seed(seed)
+        F_half = n_fft // 2 + 1
+        Bk = max(4, int(math.sqrt(F_half)))
+        anchors = torch.randn(Bsz, G, Bk, dtype=torch.cfloat)
+        mr = ref.ComplexModReLU(F_half * G)
+        with torch.no_grad():
+            mr.bias.copy_(-0.1 + 0.6 * torch.randn(F_half * G))
+            up = ref.interp_complex_1d(anchors, size=F_half, mode="cubic")
+            gate = mr(up.reshape(Bsz, -1)).view_as(up)
+            ang1 = torch.rand(1, F_half) * 6.28
+            angB = torch.rand(Bsz, F_half) * 6.28
+            pos1, posB = torch.polar(torch.ones_like(ang1), ang1), torch.polar(torch.ones_like(angB), angB)
+            gate_pos1 = gate * pos1.unsqueeze(1)        # spectre.py:536 (pos_phase.dim() == 2)
+            gate_posB = gate * posB.unsqueeze(1)
+        np.savez_compressed(os.path.join(OUT, name + ".npz"), anchors=anchors.numpy(), bias=mr.bias.detach().numpy(),
+                            eps=mr.eps.numpy(), interp=up.numpy(), gate=gate.numpy(), pos1=pos1.numpy(), posB=posB.numpy(),
+                            gate_pos1=gate_pos1.numpy(), gate_posB=gate_posB.numpy(), n_fft=np.int64(n_fft))
+        print(f"{name}: anchors{tuple(anchors.shape)} -> gate{tuple(gate.shape)}")
 
 
 if __name__ == "__main__":

@@ -157,3 +157,62 @@ def cache_update(prefix_fft: torch.Tensor, V_buf: torch.Tensor, v_t: torch.Tenso
         prefix_fft -= torch.exp(1j * omega * freq_k * j).unsqueeze(-1) * V_buf[j]
     prefix_fft += torch.exp(1j * omega * freq_k * t).unsqueeze(-1) * v_t
     V_buf[j] = v_t
+
+
+# --------------------------------------------------------------------------
+# Gate generator tail; same "test infrastructure" rule.
+# --------------------------------------------------------------------------
+def gate_tail(anchors: torch.Tensor, bias: torch.Tensor, eps: torch.Tensor,
+              pos_phase: Optional[torch.Tensor], F_half: int) -> torch.Tensor:
+    """``spectre.py:526-536`` through the same library call sites the reference uses.
+
+    anchors (B, G, Bk) complex; bias (G*F_half,) or (G, F_half); eps scalar tensor or (G,).
+    Cubic interpolation = ``F.grid_sample(..., mode="bicubic", padding_mode="border", align_corners=True)`` over a
+    height-1 image sampled at ``linspace(-1, 1, F_half)`` (``spectre.py:41-52``), then modReLU (``:109-121``), then the
+    positional phase (``:534-536``).  NB ``:41`` reshapes a (B, 2, G, K) stack to (B*G, 2, 1, K): the planes of output
+    row j are rows 2j, 2j+1 of [re_0..re_{G-1}, im_0..im_{G-1}], not (re_j, im_j) -- part of the reference's behaviour.
+    """
+    B, G, K = anchors.shape
+    planes = torch.stack([anchors.real, anchors.imag], dim=1).reshape(B * G, 2, 1, K)          # :41
+    gx = torch.linspace(-1, 1, F_half).view(1, 1, F_half, 1).expand(B * G, 1, F_half, 1)       # :45-46
+    grid = torch.cat([gx, torch.zeros_like(gx)], dim=-1)                                       # :48
+    s = torch.nn.functional.grid_sample(planes, grid, mode="bicubic", padding_mode="border", align_corners=True)  # :51
+    up = torch.complex(s[:, 0, 0, :], s[:, 1, 0, :]).view(B, G, F_half)                        # :55-60
+    mag = torch.abs(up)                                                                        # :110
+    e = eps.reshape(-1, 1) if eps.dim() else eps
+    scale = torch.relu(mag + bias.reshape(G, F_half)) / torch.sqrt(mag.square() + e.square())  # :115-118
+    g = up * scale                                                                             # :121
+    if pos_phase is not None:
+        g = g * pos_phase.unsqueeze(1 if pos_phase.dim() == 2 else 0)                          # :534-536
+    return g
+
+
+def gate_tail_direct(anchors, bias, eps, pos_phase, F_half: int, dtype="float64"):
+    """Independent numpy restatement of the same function from the published definitions (no grid_sample call):
+    Keys cubic convolution with A = -0.75, taps floor-1 .. floor+2 clamped to the border, sample positions
+    ``k * (Bk - 1) / (F_half - 1)`` (what ``linspace(-1, 1)`` un-normalised with ``align_corners=True`` means)."""
+    import numpy as np
+    a = np.asarray(anchors).astype(np.complex128 if dtype == "float64" else np.complex64)
+    B, G, K = a.shape
+    k = np.arange(F_half, dtype=np.float64)
+    ix = k * (K - 1) / (F_half - 1)
+    fl = np.floor(ix)
+    t = ix - fl
+    A = -0.75
+    c1 = lambda x: ((A + 2) * x - (A + 3)) * x * x + 1          # |x| <= 1
+    c2 = lambda x: ((A * x - 5 * A) * x + 8 * A) * x - 4 * A    # 1 < |x| < 2
+    w = [c2(t + 1), c1(t), c1(1 - t), c2(2 - t)]
+    rows = np.concatenate([a.real, a.imag], axis=1)            # (B, 2G, K): the list R of spectre.py:41's stack
+    planes = np.zeros((B, 2 * G, F_half))
+    for j in range(4):
+        idx = np.clip(fl.astype(np.int64) - 1 + j, 0, K - 1)
+        planes += rows[:, :, idx] * w[j]
+    up = planes[:, 0::2] + 1j * planes[:, 1::2]                # ... reshaped to (B*G, 2, 1, K): row j = (R[2j], R[2j+1])
+    mag = np.abs(up)
+    e = np.asarray(eps, dtype=np.float64).reshape(-1, 1) if np.ndim(eps) else float(eps)
+    scale = np.maximum(mag + np.asarray(bias, dtype=np.float64).reshape(G, F_half), 0) / np.sqrt(mag ** 2 + e ** 2)
+    g = up * scale
+    if pos_phase is not None:
+        p = np.asarray(pos_phase)
+        g = g * (p[:, None, :] if p.ndim == 2 else p)
+    return g

@@ -321,6 +321,65 @@ def test_multihead_matches_per_head_calls(fb, dev):
     assert (fused - loop).norm() / loop.norm() < 1e-5
 
 
+# --------------------------------------------------------------------------- gate generator tail
+@pytest.mark.parametrize("name", golden_names("gate_"))
+def test_gate_expand_matches_reference_goldens(name, fb, dev):
+    """Cubic interpolation + modReLU + positional phase in one launch vs the reference's own functions (goldens)."""
+    g = load_golden(name)
+    F_half = int(g["n_fft"]) // 2 + 1
+    a = torch.from_numpy(g["anchors"]).to(dev)
+    G = a.shape[1]
+    bias = torch.from_numpy(g["bias"]).to(dev).view(G, F_half)
+    eps = torch.from_numpy(g["eps"]).to(dev).reshape(1).expand(G)
+    for key, pos in (("gate", None), ("gate_pos1", g["pos1"]), ("gate_posB", g["posB"]), ("gate_pos1", g["pos1"][0])):
+        p = None if pos is None else torch.from_numpy(pos).to(dev)
+        got = torch.view_as_real(fb.gate_expand(a, bias, eps, p, F_half=F_half, G=G))
+        _check(got, torch.view_as_real(torch.from_numpy(g[key])).numpy(), rl2=5e-6, mabs=2e-5)
+    # several heads stacked: the row shuffle of spectre.py:41 stays inside each head
+    a2 = torch.cat([a, a.flip(1)], dim=1)
+    got = fb.gate_expand(a2, torch.cat([bias, bias]), torch.cat([eps, eps]), None, F_half=F_half, G=G)
+    _check(torch.view_as_real(got[:, :G]), torch.view_as_real(torch.from_numpy(g["gate"])).numpy(), rl2=5e-6, mabs=2e-5)
+
+
+def test_gate_expand_autograd(fb, oracle, dev):
+    torch.manual_seed(40)
+    a = torch.randn(2, 8, 11, dtype=torch.cfloat)
+    bias = -0.1 + 0.3 * torch.randn(8, 65)
+    eps = torch.full((8,), 1e-4)
+    w = torch.randn(2, 8, 65, dtype=torch.cfloat)
+    ac, bc = a.clone().requires_grad_(True), bias.clone().requires_grad_(True)
+    ref = torch.cat([oracle.gate_tail(ac[:, i:i + 4], bc[i:i + 4], eps[i:i + 4], None, 65) for i in (0, 4)], dim=1)
+    (ref * w).real.sum().backward()
+    ag, bg = a.to(dev).requires_grad_(True), bias.to(dev).requires_grad_(True)
+    got = fb.gate_expand(ag, bg, eps.to(dev), None, F_half=65, G=4)
+    (got * w.to(dev)).real.sum().backward()
+    _check(torch.view_as_real(ag.grad), torch.view_as_real(ac.grad).numpy(), rl2=1e-5, mabs=1e-4)
+    _check(bg.grad, bc.grad.numpy(), rl2=1e-5, mabs=1e-4)
+
+
+def test_batched_gate_generator_matches_stock_per_head_ops(fb, dev):
+    """All-heads gate generator (batched GEMMs + one expansion launch) vs the stock per-head op sequence of
+    spectre.py:511-536 run on the same device."""
+    import fft_b200.modules as M
+    torch.manual_seed(41)
+    mh = fb.SpectreMultiHead(768, 12, 1024, pooling_type="mean", wavelet_on_rate=0.0).to(dev).eval()
+    x = torch.randn(2, 1024, 768, device=dev)
+    with torch.no_grad():
+        for h in mh.heads:
+            h.modrelu.bias.add_(0.3 * torch.randn_like(h.modrelu.bias))
+        Q_all = torch.stack([h.W_q(c) for h, c in zip(mh.heads, torch.chunk(x, 12, -1))], dim=2)
+        gate, q_pool = M.multihead_gate(mh, Q_all, None)
+        stock = []
+        for i, h in enumerate(mh.heads):
+            qp = h.q_norm(Q_all[:, :, i].mean(1))
+            anc = torch.view_as_complex(h.gate_mlp(qp).view(2, h.G, h.B, 2))
+            up = M.interp_complex_1d(anc, size=h.F_half, mode="cubic")
+            stock.append(h.modrelu(up.reshape(2, -1)).view_as(up))
+        stock = torch.cat(stock, dim=1)
+    assert gate.shape == stock.shape == (2, 48, 513)
+    _check(torch.view_as_real(gate), torch.view_as_real(stock).cpu().numpy(), rl2=2e-5, mabs=1e-4)
+
+
 # --------------------------------------------------------------------------- decode side (SURVEY 8f-1)
 def test_decode_sequence_matches_reference(fb, dev):
     """Prompt of 200 tokens then 100 single-token steps (eviction after t >= 256) against the outputs of the stock

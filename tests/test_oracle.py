@@ -125,3 +125,65 @@ def test_cache_update_restatement_matches_reference_sequence():
         oracle.cache_update(prefix, V_buf, vs[i], t, n)
     assert t == int(g["t"])
     assert np.array_equal(prefix.numpy(), g["prefix_fft"])
+
+
+# --------------------------------------------------------------------------- gate generator tail
+GATE_CASES = golden_names("gate_")
+
+
+@pytest.mark.parametrize("name", GATE_CASES)
+def test_gate_tail_oracle_matches_reference_goldens(name):
+    g = load_golden(name)
+    F_half = int(g["n_fft"]) // 2 + 1
+    a, bias, eps = _t(g["anchors"]), _t(g["bias"]), _t(g["eps"])
+    # same library call sites as spectre.py:41-60, :110-121, :536 -> bit for bit
+    assert np.array_equal(oracle.gate_tail(a, bias, eps, None, F_half).numpy(), g["gate"])
+    assert np.array_equal(oracle.gate_tail(a, bias, eps, _t(g["pos1"]), F_half).numpy(), g["gate_pos1"])
+    assert np.array_equal(oracle.gate_tail(a, bias, eps, _t(g["posB"]), F_half).numpy(), g["gate_posB"])
+
+
+def _crel(a, b):
+    return float(np.linalg.norm(np.asarray(a) - np.asarray(b)) / np.linalg.norm(np.asarray(b)))
+
+
+@pytest.mark.parametrize("name", GATE_CASES)
+def test_gate_tail_direct_restatement_matches_reference_goldens(name):
+    """Keys cubic convolution (A = -0.75, border clamp, align_corners) written out == what grid_sample evaluates."""
+    g = load_golden(name)
+    F_half = int(g["n_fft"]) // 2 + 1
+    a = g["anchors"]
+    up = oracle.gate_tail_direct(a, np.zeros_like(g["bias"]), 0.0, None, F_half)   # scale = |z| / |z| = 1 -> pure interpolation
+    assert _crel(up, g["interp"]) < 3e-6      # the reference's float32 sample positions cost ~1e-6 against exact ones
+    for key, pos in (("gate", None), ("gate_pos1", g["pos1"]), ("gate_posB", g["posB"])):
+        y = oracle.gate_tail_direct(a, g["bias"], g["eps"], pos, F_half)
+        assert _crel(y, g[key]) < 3e-6 and np.abs(y - g[key]).max() < 1e-5 * np.abs(g[key]).max()
+
+
+def test_batched_gate_generator_equals_per_head_loop(monkeypatch):
+    """Host logic of the all-heads gate generator (pool -> LayerNorm -> MLP as batched GEMMs over stacked head weights)
+    against the per-head generator, on CPU with the expansion kernel replaced by its stock-PyTorch statement."""
+    import fft_b200.modules as M
+    from fft_b200 import ops
+    monkeypatch.setattr(M, "gate_expand",
+                        lambda a, b, e, p=None, *, F_half, G: ops._gate_expand_torch(a, b, e, p, F_half, G))
+    torch.manual_seed(3)
+    mh = M.SpectreMultiHead(48, 3, 128, pooling_type="mean", wavelet_on_rate=0.0, num_groups=4).eval()
+    with torch.no_grad():
+        for h in mh.heads:
+            h.modrelu.bias.add_(0.3 * torch.randn_like(h.modrelu.bias))
+    assert M._heads_batchable(mh)
+    x = torch.randn(2, 100, 48)
+    pos = torch.polar(torch.ones(2, 65), torch.rand(2, 65) * 6.28)
+    with torch.no_grad():
+        Q_all = torch.stack([h.W_q(c) for h, c in zip(mh.heads, torch.chunk(x, 3, -1))], dim=2)
+        for p in (pos, pos[:1], None):
+            gate, q_pool = M.multihead_gate(mh, Q_all, p)
+            per = [M.head_gate(h, Q_all[:, :, i], p) for i, h in enumerate(mh.heads)]
+            assert _crel(gate.numpy(), torch.cat([g for g, _ in per], 1).numpy()) < 1e-5
+            assert torch.allclose(q_pool, torch.cat([q for _, q in per], -1), atol=1e-5)
+    # cached stacks follow in-place parameter updates
+    with torch.no_grad():
+        mh.heads[1].gate_mlp[2].bias.add_(1.0)
+        gate2, _ = M.multihead_gate(mh, Q_all, None)
+        per2 = torch.cat([M.head_gate(h, Q_all[:, :, i], None)[0] for i, h in enumerate(mh.heads)], 1)
+    assert _crel(gate2.numpy(), per2.numpy()) < 1e-5 and _crel(gate2.numpy(), gate.numpy()) > 1e-3

@@ -23,4 +23,10 @@ with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
     e1.record()
     torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / 5
+if len(sys.argv) > 2 and sys.argv[2] == "profile":
+    from torch.profiler import ProfilerActivity, profile
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16), profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
+        model(tok, return_hidden=True)
+        torch.cuda.synchronize()
+    print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=25, max_name_column_width=60))
 print(f"Spectre-base bf16 fwd: B={B} seq=4096: {ms:.2f} ms/step, {B * 4096 / ms * 1e3:.3e} tokens/s")
