@@ -33,6 +33,7 @@ SYMBOLS = (
     "spectre_mix_set_timeline",
     "spectre_mix_set_tmem",
     "spectre_mix_set_skew_ns",
+    "spectre_mix_set_sched",
     "spectre_mix_set_two_pass",
 )
 
@@ -101,6 +102,8 @@ def load():
         lib.spectre_mix_set_two_pass.argtypes = [i32]
         lib.spectre_mix_set_skew_ns.restype = i32
         lib.spectre_mix_set_skew_ns.argtypes = [i32]
+        lib.spectre_mix_set_sched.restype = i32
+        lib.spectre_mix_set_sched.argtypes = [i32]
         lib.spectre_mix_set_tmem.restype = i32
         lib.spectre_mix_set_tmem.argtypes = [i32]
         lib.spectre_mix_set_timeline.restype = i32

@@ -42,10 +42,11 @@ int cuda_fail(cudaError_t e, const char *what) {
 }
 
 int g_tile_channels_override = 0;
-int g_prefetch = 1;   // L2 prefetch of the tile after next by the TMA unit (helps the TMEM-staged variant, neutral elsewhere)
+int g_prefetch = 0;   // L2 prefetch of the next tiles: 0 off (default: the TMA unit is the busiest part of the TMEM variant), 1 TMA prefetch, 2 cooperative whole-line prefetch (needs -DSPX_COOP_PF=1)
 int g_use_tma = 1;
 int g_use_tmem = 1;
-int g_skew_ns = 0;
+int g_skew_ns = -300;   // warp stagger after the CTA barriers (see stagger() in the kernel header)
+int g_sched = 3;          // bit 0 stagger before the last inverse pass too, bit 1 split barrier around its read
 int g_use_two_pass = 1;
 unsigned long long *g_timeline = nullptr;
 
@@ -315,7 +316,8 @@ int mix_two_pass(DeviceState &st, const KernelEntry &k, const void *v, int dtype
     p.inv_n = 1.0f / (float)n_fft;
     p.prefetch = g_prefetch;
     p.timeline = nullptr;
-    p.skew_ns = 0;
+    p.skew_ns = g_skew_ns;
+    p.sched = g_sched;
     p.sub_R = R;
     Choice c;
     c.k = &k;
@@ -352,7 +354,7 @@ int spectre_mix_set_tile_channels(int tile_channels) {
 }
 
 int spectre_mix_set_prefetch(int enable) {
-    g_prefetch = enable ? 1 : 0;
+    g_prefetch = enable < 0 ? 0 : enable;   // 0 off, 1 TMA prefetch of the next tiles, 2 cooperative whole-line prefetch (TMEM variant)
     return 0;
 }
 
@@ -366,8 +368,13 @@ int spectre_mix_set_two_pass(int enable) {
     return 0;
 }
 
-int spectre_mix_set_skew_ns(int ns) {
-    g_skew_ns = ns < 0 ? 0 : ns;
+int spectre_mix_set_skew_ns(int code) {
+    g_skew_ns = code;
+    return 0;
+}
+
+int spectre_mix_set_sched(int flags) {
+    g_sched = flags;
     return 0;
 }
 
@@ -437,6 +444,7 @@ int spectre_mix_fwd(const void *v, int v_dtype, int64_t v_stride_b, int64_t v_st
     p.prefetch = g_prefetch;
     p.timeline = g_timeline;
     p.skew_ns = g_skew_ns;
+    p.sched = g_sched;
     p.sub_R = 1;
 
     // TMA-fed variant when V's layout can be described to the TMA unit; otherwise direct 128-bit global loads

@@ -52,7 +52,9 @@ struct MixParams {
     float inv_n;
     int prefetch;         // 1: prefetch the CTA's next tile into L2 while this one is transformed
     int sub_R;            // long-context path: number of interleaved sub-transforms (n_total = sub_R * n_fft), else 1
-    int skew_ns;          // experiment: delay half of the warps by this much before the warp-local passes
+    int skew_ns;          // warp stagger code (see stagger()): 0 off, > 0 legacy nanosleep, < 0 clock spin per scheduler slot
+    int sched;            // bit 0: stagger also after the barrier before inverse stage 0; bit 1 (TMEM variant): split barrier
+                          // around the inverse stage-0 read (arrive after the read, wait before the next tile's stage-0 write)
     unsigned long long *timeline;  // optional: per-CTA phase timestamps (ns) for tools/timeline.py, else nullptr
 };
 
@@ -62,7 +64,7 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
     return t;
 }
 constexpr int kTimelineSlots = 8;     // timestamps per tile
-constexpr int kTimelineTiles = 8;     // tiles recorded per CTA
+constexpr int kTimelineTiles = 8;     // tiles recorded per CTA (by thread 0 of each of the up to four 128-thread groups)
 
 // ------------------------------------------------------------------ packed / scalar lanes
 __device__ __forceinline__ float2 vadd(float2 a, float2 b) { return __fadd2_rn(a, b); }
@@ -211,6 +213,18 @@ __host__ __device__ constexpr int cmax(int a, int b) { return a > b ? a : b; }
 // ring of TMA boxes shared by both directions of the TMEM variant: while a tile is parked all but one slot hold
 // loads in flight (latency cover), while results are drained all of them are store sources
 constexpr int kTmemSlots = 5;
+// register split of the TMEM variant (512 compute + 128 helper threads, 96 per thread at launch = 61440 in the CTA pool)
+#ifndef SPX_COOP_PF
+#define SPX_COOP_PF 0
+#endif
+#ifndef SPX_GATE_ASYNC
+#define SPX_GATE_ASYNC 0
+#endif
+#ifndef SPX_TMEM_COMPUTE_REGS
+#define SPX_TMEM_COMPUTE_REGS 112
+#endif
+constexpr int kTmemComputeRegs = SPX_TMEM_COMPUTE_REGS, kTmemHelperRegs = (96 * 640 - SPX_TMEM_COMPUTE_REGS * 512) / 128;
+static_assert(kTmemHelperRegs % 8 == 0 && kTmemHelperRegs >= 24, "setmaxnreg takes multiples of 8");
 
 // Which stages keep their twiddles in shared memory: all of them while the tables fit beside the tile; from
 // n_fft = 8192 the (largest) stage-0 table is read through L2 instead, at 16384 every table is.
@@ -509,6 +523,24 @@ __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void helper_bar() { asm volatile("bar.sync 2, 128;" ::: "memory"); }
+// Warp stagger: the four warps that share a scheduler (warp id / 4 = "slot" 0..3) leave a CTA barrier in lock step and would
+// all load, then all compute, then all store.  Holding slot s back by s * clk cycles lets the shared-memory phase of one warp
+// run under the butterflies of another.  code > 0: legacy nanosleep of slots 1 and 3; code < 0: clock spin, |code| % 100000
+// cycles per step, |code| / 100000 selects the grouping (0: four steps, 1: slots {0,1} vs {2,3}, 2: even vs odd slots).
+__device__ __forceinline__ void stagger(int code, int tid) {
+    if (code == 0) return;
+    if (code > 0) {
+        if ((tid >> 7) & 1) __nanosleep(code);
+        return;
+    }
+    const int a = -code, grp = a / 100000, clk = a % 100000;
+    int slot = (tid >> 7) & 3;
+    if (grp == 1) slot >>= 1;
+    else if (grp == 2) slot &= 1;
+    const int target = slot * clk;
+    const int t0 = (int)clock();
+    while ((int)clock() - t0 < target) {}
+}
 
 // landing-buffer element (one tile element as TMA delivers it: CH consecutive channels of one row)
 template <int MODE, class IO>
@@ -581,6 +613,30 @@ __device__ __forceinline__ void gate_put(float2 *gs, const float2 (&gv)[GK], int
         if (k <= N / 2) {
             const float im = (k == 0 || k == N / 2) ? 0.f : gv[j].y * inv_n;
             gs[k + (k >> 4)] = make_float2(gv[j].x * inv_n, im);
+        }
+    }
+}
+
+// gate row -> padded shared table by asynchronous 8-byte copies (LDGSTS): no registers are held while the row is in flight.
+// Once its copies have landed each thread rescales its own entries in place (1/n_fft, imag(DC) = imag(Nyquist) = 0).
+template <int N, int NT, int GK>
+__device__ __forceinline__ void gate_copy_async(float2 *gs, const float2 *gp, int tid) {
+#pragma unroll
+    for (int j = 0; j < GK; ++j) {
+        const int k = tid + j * NT;
+        if (k <= N / 2)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(gs + k + (k >> 4))), "l"(gp + k) : "memory");
+    }
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+template <int N, int NT, int GK>
+__device__ __forceinline__ void gate_scale_own(float2 *gs, int tid, float inv_n) {
+#pragma unroll
+    for (int j = 0; j < GK; ++j) {
+        const int k = tid + j * NT;
+        if (k <= N / 2) {
+            const float2 g = gs[k + (k >> 4)];
+            gs[k + (k >> 4)] = make_float2(g.x * inv_n, (k == 0 || k == N / 2) ? 0.f : g.y * inv_n);
         }
     }
 }
@@ -752,6 +808,7 @@ __global__ void __launch_bounds__(NT + ((TMA_IN && NT >= kSepProducerMinThreads)
             mbar_init(bar_in_free, NW);
             mbar_init(bar_out_full, NW);
             mbar_init(bar_out_free, 1);
+            mbar_init(bar + 80, NW);                                  // inverse stage-0 read done (split barrier, sched bit 1)
 #pragma unroll
             for (int i = 0; i < kTmemSlots; ++i) mbar_init(bar_landed + 8 * i, 1);
         }
@@ -761,96 +818,125 @@ __global__ void __launch_bounds__(NT + ((TMA_IN && NT >= kSepProducerMinThreads)
         tc_fence_after();
         tmem_base = *tmem_base_s;
         if (tid >= NT) {
-            asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(helper_regs(NT, MINB)));
+            asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kTmemHelperRegs));
             const int hl = tid - NT;                              // 0..127 = TMEM lane this helper thread serves
             const uint32_t tq = tmem_base + ((uint32_t)(hl & ~31) << 16);
-            uint32_t land_cnt = 0;                                // boxes consumed so far (slot = cnt % slots, phase = cnt / slots)
-            uint32_t store_cnt = 0;                               // TMA store groups committed by the elected thread
-            constexpr int NBOX = N / kTmaBoxRows;
-            auto issue_box = [&](int tb, int tc, int k, uint32_t seq) {   // elected thread: box k of a tile -> slot seq % slots
-                const uint32_t sl = seq % kTmemSlots;
+            constexpr int NBOX = N / kTmaBoxRows;                 // TMA boxes per tile
+            constexpr int GPB = kTmaBoxRows * NCOL / 128;         // 128-element groups per box
+#ifndef SPX_TMEM_SP
+#define SPX_TMEM_SP 1
+#endif
+            constexpr int SP = SPX_TMEM_SP;                       // TMA stores allowed to be still reading their slot
+            constexpr int DEPTH = kTmemSlots - SP;                // loads kept in flight
+            const bool idle = (p.sched & 8) != 0;                 // diagnostic: no tile I/O at all (results invalid)
+            // The helper works in phases.  Phase P parks tile P of this CTA in TMEM-IN and drains tile P - 2 from TMEM-OUT,
+            // one TMA box each per step, through ONE ring: a slot receives a load, is read out into tensor memory, is refilled
+            // by the same threads with a box of results, leaves through a TMA store and then takes the next load.  Loads
+            // therefore stay in flight while results drain (DEPTH boxes ahead), and the load stream runs across tile
+            // boundaries.  Load box idx (stream index over all tiles of this CTA) is consumed at step idx, in slot idx % slots.
+            const int my_tiles = ((int)blockIdx.x < p.num_tiles && !idle) ? (p.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+            const int total_boxes = my_tiles * NBOX;
+            // load stream state (used by the elected thread): next box to issue, kept incrementally -- the elected thread's
+            // path between two barriers is the helper's critical path, so no divisions there except once per tile
+            int ld_left = total_boxes, ld_k = 0, ld_t = (int)blockIdx.x, ld_tb = 0, ld_tc = 0;
+            uint32_t ld_slot = 0;
+            if (my_tiles > 0) {
+                ld_tb = ld_t / p.tiles_per_row;
+                ld_tc = (ld_t - ld_tb * p.tiles_per_row) * NCOL * CH;
+            }
+            auto issue_next = [&]() {                             // elected thread: next box of the stream -> next slot
                 fence_proxy_async();
-                mbar_expect_tx(bar_landed + 8 * sl, SLOTB);
-                tma_load_3d(smem_u32(stg) + sl * SLOTB, &tmap, tc, k * kTmaBoxRows, tb, bar_landed + 8 * sl);
-            };
-            // park tile t in TMEM-IN: TMA boxes through the load slots (kTmemSlots - 1 boxes always in flight),
-            // two rows per helper thread and box
-            auto park_tile = [&](int t) {
-                const int tb = t / p.tiles_per_row;
-                const int tc = (t - tb * p.tiles_per_row) * NCOL * CH;
-                if (hl == 0) {
-                    tma_wait_read<0>();                            // stores of the previous drain have left the ring
-#pragma unroll
-                    for (int k = 0; k < kTmemSlots - 1; ++k) issue_box(tb, tc, k, land_cnt + k);
+                mbar_expect_tx(bar_landed + 8 * ld_slot, SLOTB);
+                tma_load_3d(smem_u32(stg) + ld_slot * SLOTB, &tmap, ld_tc, ld_k * kTmaBoxRows, ld_tb, bar_landed + 8 * ld_slot);
+                --ld_left;
+                ld_slot = (ld_slot + 1 == kTmemSlots) ? 0 : ld_slot + 1;
+                if (++ld_k == NBOX) {
+                    ld_k = 0;
+                    ld_t += (int)gridDim.x;
+                    ld_tb = ld_t / p.tiles_per_row;
+                    ld_tc = (ld_t - ld_tb * p.tiles_per_row) * NCOL * CH;
                 }
+            };
+            if (hl == 0) {
+                for (int i = 0; i < DEPTH && ld_left > 0; ++i) issue_next();
+                if (p.prefetch == 1 && my_tiles > 1) prefetch_tile((int)blockIdx.x + (int)gridDim.x);
+            }
+            // prefetch == 2: the four CTAs that work on four adjacent channel tiles pull the NEXT tiles' rows into L2 as whole
+            // 128-byte lines (one quarter of the rows each), so DRAM sees full-line reads instead of 32-byte pieces
+#if SPX_COOP_PF
+            const bool coop_pf = (p.prefetch == 2) && (p.tiles_per_row % 4 == 0) && (gridDim.x % 4 == 0) && (NCOL * CH == 8) &&
+                                 (sizeof(TIN) == 4) && (p.n_in == N) && hl < 64;
+#endif
+            uint32_t sl = 0, landed_par = 0;                      // ring slot of the current step; one landed-parity bit per slot
+            const int phases = my_tiles > 0 ? my_tiles + 2 : 0;
 #pragma unroll 1
-                for (int k = 0; k < NBOX; ++k) {
-                    // the slot box k + slots - 1 goes to was emptied before the helper barrier of the previous iteration
-                    if (hl == 0 && k + kTmemSlots - 1 < NBOX) issue_box(tb, tc, k + kTmemSlots - 1, land_cnt + kTmemSlots - 1);
-                    const uint32_t sl = land_cnt % kTmemSlots;
-                    mbar_wait(bar_landed + 8 * sl, (land_cnt / kTmemSlots) & 1);
-                    ++land_cnt;
-                    const float4 *slot = reinterpret_cast<const float4 *>(stg + sl * SLOTB);
-                    constexpr int GPB = kTmaBoxRows * NCOL / 128;  // 128-element groups per box
-                    float4 v[GPB];
-#pragma unroll
-                    for (int g = 0; g < GPB; ++g) v[g] = slot[g * 128 + hl];      // consecutive lanes, consecutive slots
-#pragma unroll
-                    for (int g = 0; g < GPB; ++g) tmem_st4(tq + (uint32_t)(4 * (k * GPB + g)), v[g].x, v[g].y, v[g].z, v[g].w);
-                    helper_bar();                                  // every helper thread has read this slot
-                }
-                tmem_wait_st();
-                tc_fence_before();
-                helper_bar();
-                if (hl == 0) mbar_arrive(bar_in_full);
-            };
-            // drain tile t from TMEM-OUT through the two store slots
-            auto drain_tile = [&](int t) {
-                const int tb = t / p.tiles_per_row;
-                const int tc = (t - tb * p.tiles_per_row) * NCOL * CH;
-#pragma unroll 1
-                for (int k = 0; k < NBOX; ++k) {
-                    const int s = k % kTmemSlots;
-                    if (hl == 0 && k >= kTmemSlots) tma_wait_read<kTmemSlots - 1>();   // the store that last used slot s has left it   // the store that last used slot s has left it
-                    helper_bar();
-                    float4 *slot = reinterpret_cast<float4 *>(stg + s * SLOTB);
-                    constexpr int GPB = kTmaBoxRows * NCOL / 128;
-                    float4 v[GPB];
-#pragma unroll
-                    for (int g = 0; g < GPB; ++g) tmem_ld4(tq + (uint32_t)(TCOLS + 4 * (k * GPB + g)), v[g].x, v[g].y, v[g].z, v[g].w);
-                    tmem_wait_ld();
-#pragma unroll
-                    for (int g = 0; g < GPB; ++g) slot[g * 128 + hl] = v[g];
-                    fence_proxy_async();
-                    helper_bar();
-                    if (hl == 0) {
-                        tma_store_3d(&tmap_out, smem_u32(slot), tc, k * kTmaBoxRows, tb);
-                        tma_commit();
-                        ++store_cnt;
-                    }
-                }
-                tc_fence_before();
-                helper_bar();
-                if (hl == 0) mbar_arrive(bar_out_free);            // TMEM-OUT may be overwritten (stores still draining smem)
-            };
-            int it = 0;
-            if ((int)blockIdx.x < p.num_tiles) park_tile(blockIdx.x);
-            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
-                const int nt = tile + gridDim.x;
-                if (nt < p.num_tiles) {
-                    mbar_wait(bar_in_free, it & 1);               // the compute warps have pulled `tile` out of TMEM-IN
-                    tc_fence_after();
-                    park_tile(nt);
-                    // and let the TMA unit pull the tile after that one into L2 (requests only, no shared memory needed)
-                    if (p.prefetch && hl == 0 && nt + (int)gridDim.x < p.num_tiles) prefetch_tile(nt + gridDim.x);
-                }
-                mbar_wait(bar_out_full, it & 1);                  // results of `tile` are parked in TMEM-OUT
+            for (int P = 0; P < phases; ++P) {
+                const bool do_park = P < my_tiles, do_drain = P >= 2;
+                if (do_park && P >= 1) mbar_wait(bar_in_free, (P - 1) & 1);    // compute warps pulled tile P-1 out of TMEM-IN
+                if (do_drain) mbar_wait(bar_out_full, (P - 2) & 1);            // results of tile P-2 sit in TMEM-OUT
                 tc_fence_after();
-                drain_tile(tile);
+                if (p.prefetch == 1 && hl == 0 && P + 2 < my_tiles) prefetch_tile((int)blockIdx.x + (P + 2) * (int)gridDim.x);
+                const int td = (int)blockIdx.x + (P - 2) * (int)gridDim.x;
+                const int tb = do_drain ? td / p.tiles_per_row : 0;
+                const int tc = do_drain ? (td - tb * p.tiles_per_row) * NCOL * CH : 0;
+                // cooperative prefetch target: rows of this CTA's tile P + 1 (its loads are issued one phase from now)
+#if SPX_COOP_PF
+                const TIN *pf = nullptr;
+                if (coop_pf && P + 1 < my_tiles) {
+                    const int tp = (int)blockIdx.x + (P + 1) * (int)gridDim.x;
+                    const int pb = tp / p.tiles_per_row, pc = tp - pb * p.tiles_per_row;
+                    pf = vbase + (long long)pb * p.v_sb + (long long)((pc & 3) * 64 + hl) * p.v_sn + (pc & ~3) * (NCOL * CH);
+                }
+#endif
+#pragma unroll 1
+                for (int k = 0; k < NBOX; ++k) {
+                    float4 *slot = reinterpret_cast<float4 *>(stg + sl * SLOTB);
+                    float4 v[GPB];
+#if SPX_COOP_PF
+                    if (pf) {
+                        prefetch_l2(pf);
+                        pf += (long long)kTmaBoxRows * p.v_sn;
+                    }
+#endif
+                    if (do_park) {
+                        mbar_wait(bar_landed + 8 * sl, (landed_par >> sl) & 1);
+                        landed_par ^= 1u << sl;
+#pragma unroll
+                        for (int g = 0; g < GPB; ++g) v[g] = slot[g * 128 + hl];      // consecutive lanes, consecutive slots
+#pragma unroll
+                        for (int g = 0; g < GPB; ++g) tmem_st4(tq + (uint32_t)(4 * (k * GPB + g)), v[g].x, v[g].y, v[g].z, v[g].w);
+                    }
+                    if (do_drain) {
+#pragma unroll
+                        for (int g = 0; g < GPB; ++g) tmem_ld4(tq + (uint32_t)(TCOLS + 4 * (k * GPB + g)), v[g].x, v[g].y, v[g].z, v[g].w);
+                        tmem_wait_ld();
+                        // every thread refills exactly the ring entries it has just read: no barrier in between
+#pragma unroll
+                        for (int g = 0; g < GPB; ++g) slot[g * 128 + hl] = v[g];
+                        fence_proxy_async();
+                    }
+                    helper_bar();                                  // slot read by all (park) / written by all (drain)
+                    if (hl == 0) {
+                        if (do_drain) {
+                            tma_store_3d(&tmap_out, smem_u32(slot), tc, k * kTmaBoxRows, tb);
+                            tma_commit();
+                            tma_wait_read<SP>();                   // the store of step - SP has left its slot ...
+                        }
+                        if (ld_left > 0) issue_next();             // ... which is where the next load of the stream lands
+                    }
+                    sl = (sl + 1 == kTmemSlots) ? 0 : sl + 1;
+                }
+                if (do_park) tmem_wait_st();
+                tc_fence_before();
+                helper_bar();
+                if (hl == 0) {
+                    if (do_park) mbar_arrive(bar_in_full);         // tile P is parked
+                    if (do_drain) mbar_arrive(bar_out_free);       // TMEM-OUT may be overwritten (stores still draining smem)
+                }
             }
             if (hl == 0) tma_wait_all();
         } else {
-            asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(compute_regs(NT, MINB)));
+            asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kTmemComputeRegs));
         }
     }
     if constexpr (TMA_IN && !TMEM_IO) {
@@ -888,8 +974,8 @@ __global__ void __launch_bounds__(NT + ((TMA_IN && NT >= kSepProducerMinThreads)
     uint32_t parity = 0;
     int tl_tile = 0;
 #define SPX_MARK(slot)                                                                                   \
-    if (p.timeline && tid == 0 && tl_tile < kTimelineTiles)                                              \
-        p.timeline[((size_t)blockIdx.x * kTimelineTiles + tl_tile) * kTimelineSlots + (slot)] = globaltimer_ns();
+    if (p.timeline && (tid & 127) == 0 && tl_tile < kTimelineTiles)                                      \
+        p.timeline[(((size_t)blockIdx.x * 4 + (tid >> 7)) * kTimelineTiles + tl_tile) * kTimelineSlots + (slot)] = globaltimer_ns();
     uint32_t rnd = 0;   // output staging rounds issued so far (buffer = rnd & 1)
     // stage-0 butterfly of (thread, iteration): channel column and row offset u.  The TMEM variant ties u to the TMEM lane
     // the thread can reach: lane = 32 * (warp % 4) + lane id = u mod 128.
@@ -916,8 +1002,8 @@ __global__ void __launch_bounds__(NT + ((TMA_IN && NT >= kSepProducerMinThreads)
         const bool full_tile = (ce0 + NCOL <= CE) && (p.n_in == N);
         SPX_MARK(0)
 
-        // ---- stage the gate tables of this tile (scaled by 1/n_fft, imag(DC)=imag(Nyquist)=0).  With one table per
-        // tile this was already done while the previous tile finished (see below); else do it here.
+        // ---- stage the gate tables of this tile (asynchronous copies, awaited before the barrier that follows stage 0).
+        // With one table per tile this was already started while the previous tile finished (see below); else do it here.
         if constexpr (!RFFT_ONLY) {
             if constexpr (SUB) {
                 if (tile == (int)blockIdx.x) {
@@ -929,9 +1015,13 @@ __global__ void __launch_bounds__(NT + ((TMA_IN && NT >= kSepProducerMinThreads)
                 for (int t = 0; t < p.gate_tables; ++t) {
                     const int g = g0 + t;
                     if (g < p.NG) {
+#if SPX_GATE_ASYNC
+                        gate_copy_async<N, NT, GK>(gate_s + t * GS, p.gate + ((long long)b * p.NG + g) * (N / 2 + 1), tid);
+#else
                         float2 gv[GK];
                         gate_fetch<N, NT, GK>(gv, p.gate + ((long long)b * p.NG + g) * (N / 2 + 1), tid);
                         gate_put<N, NT, GK>(gate_s + t * GS, gv, tid, p.inv_n);
+#endif
                     }
                 }
             }
@@ -943,7 +1033,7 @@ __global__ void __launch_bounds__(NT + ((TMA_IN && NT >= kSepProducerMinThreads)
             if constexpr (TMEM_IO) {
                 // the helper warpgroup parked this tile in TMEM-IN: row u + L0 m sits in lane u % 128, column group
                 // (u / 128 + G128 m); this warp's 32 lanes are exactly its 32 values of u
-                mbar_wait(bar, tile_it & 1);
+                if (!(p.sched & 8)) mbar_wait(bar, tile_it & 1);
                 tc_fence_after();
                 SPX_MARK(1)
                 int col, u;
@@ -956,6 +1046,21 @@ __global__ void __launch_bounds__(NT + ((TMA_IN && NT >= kSepProducerMinThreads)
                 tc_fence_before();
                 __syncwarp();
                 if ((tid & 31) == 0) mbar_arrive(bar + 8);   // TMEM-IN consumed by this warp
+                if (p.sched & 4) {
+                    // diagnostic: tile I/O only -- hand the tile straight back to the helper warpgroup (results invalid)
+                    if (tile_it >= 1) mbar_wait(bar + 24, (tile_it - 1) & 1);
+                    tc_fence_after();
+                    const uint32_t tb_ = ta + (uint32_t)TCOLS;
+#pragma unroll
+                    for (int m = 0; m < R0; ++m)
+                        tmem_st4(tb_ + (uint32_t)(m * G128 * CPR), x0[0][m].re.x, x0[0][m].re.y, x0[0][m].im.x, x0[0][m].im.y);
+                    tmem_wait_st();
+                    tc_fence_before();
+                    __syncwarp();
+                    if ((tid & 31) == 0) mbar_arrive(bar + 16);
+                    ++tile_it;
+                    continue;
+                }
             } else if constexpr (TMA_IN) {
                 mbar_wait(bar, parity);
                 parity ^= 1;
@@ -1013,17 +1118,27 @@ __global__ void __launch_bounds__(NT + ((TMA_IN && NT >= kSepProducerMinThreads)
                         const float2 wq = tw_get<PL, 0>(tw, p.tw, (q - 1) * L0 + u);
                         x0[it][q] = cmul(x0[it][q], wq.x, wq.y);
                     }
+                    if constexpr (TMEM_IO) {
+                        // split barrier: every warp has pulled the previous tile's last pass out of the buffer
+                        if ((p.sched & 2) && tile_it >= 1) mbar_wait(bar + 80, (tile_it - 1) & 1);
+                    }
                     S *cb = buf + col * CS + u + (u >> 4);
 #pragma unroll
                     for (int q = 0; q < R0; ++q) cb[q * L0 + ((q * L0) >> 4)] = E::pack(x0[it][q]);
                 }
             }
         }
+        if constexpr (!RFFT_ONLY && !SUB && SPX_GATE_ASYNC) {
+            // this thread's share of the gate tables has landed: rescale it in place before the barrier publishes it
+            cp_async_wait_all();
+            for (int t = 0; t < p.gate_tables; ++t)
+                if (g0 + t < p.NG) gate_scale_own<N, NT, GK>(gate_s + t * GS, tid, p.inv_n);
+        }
         cta_sync<NT, SEP>();
         SPX_MARK(2)
         // stagger: with every warp in lock step all of them load, then all compute, then all store; holding back two of
         // the four warps of each scheduler lets their shared-memory phases overlap the others' butterflies
-        if (p.skew_ns > 0 && ((tid >> 7) & 1)) __nanosleep(p.skew_ns);
+        if constexpr (TMEM_IO) stagger(p.skew_ns, tid);
 
         // ---- forward stages 1 .. NS-2: smem -> butterfly -> twiddle -> smem (in place)
         // The exchange between stage NS-2 and the middle pass is a 16x16 transpose among the 16 threads that share
@@ -1107,7 +1222,7 @@ __global__ void __launch_bounds__(NT + ((TMA_IN && NT >= kSepProducerMinThreads)
 
         // the gate table is free again: start fetching the next tile's gate row, park it in registers
         // across the inner inverse passes, and publish it before the last pass
-        float2 gnext[SUB ? GKS : GK];
+        float2 gnext[SUB ? GKS : (SPX_GATE_ASYNC ? 1 : GK)];
         const int tile_next = tile + gridDim.x;
         const bool fetch_next = gate_early && tile_next < p.num_tiles;
         int nq = 0;
@@ -1119,7 +1234,9 @@ __global__ void __launch_bounds__(NT + ((TMA_IN && NT >= kSepProducerMinThreads)
                 gate_fetch_sub<N, NT, GKS>(gnext, p.gate + ((long long)(nrow / p.sub_R) * p.NG + ng) * ((N * p.sub_R) / 2 + 1), tid, nq,
                                            p.sub_R);
             } else {
+#if !SPX_GATE_ASYNC
                 gate_fetch<N, NT, GK>(gnext, p.gate + ((long long)nrow * p.NG + ng) * (N / 2 + 1), tid);
+#endif
             }
         }
 
@@ -1127,10 +1244,21 @@ __global__ void __launch_bounds__(NT + ((TMA_IN && NT >= kSepProducerMinThreads)
         if constexpr (NS > 3) { inv_inner_pass<PL, MODE, NCOL, NT, 2>(buf, tw, p.tw, tid); cta_sync<NT, SEP>(); }
         if constexpr (NS > 2) { inv_inner_pass<PL, MODE, NCOL, NT, 1>(buf, tw, p.tw, tid); cta_sync<NT, SEP>(); }
         if (fetch_next) {
-            if constexpr (SUB) gate_put_sub<N, NT, GKS>(gate_s, gnext, tid, nq, p.sub_R, p.inv_n);
-            else gate_put<N, NT, GK>(gate_s, gnext, tid, p.inv_n);
+            if constexpr (SUB) {
+                gate_put_sub<N, NT, GKS>(gate_s, gnext, tid, nq, p.sub_R, p.inv_n);
+            } else {
+#if SPX_GATE_ASYNC
+                // every warp is past the middle pass: the next tile's gate row may stream into the table
+                const int nrow = tile_next / p.tiles_per_row;
+                const int ng = ((tile_next - nrow * p.tiles_per_row) * NCOL * CH) / p.group_width;
+                gate_copy_async<N, NT, GK>(gate_s, p.gate + ((long long)nrow * p.NG + ng) * (N / 2 + 1), tid);
+#else
+                gate_put<N, NT, GK>(gate_s, gnext, tid, p.inv_n);
+#endif
+            }
         }
         SPX_MARK(5)
+        if constexpr (TMEM_IO) { if (p.sched & 1) stagger(p.skew_ns, tid); }
 
         // ---- inverse stage 0: smem -> twiddle -> butterfly -> global
         {
@@ -1148,7 +1276,12 @@ __global__ void __launch_bounds__(NT + ((TMA_IN && NT >= kSepProducerMinThreads)
             }
             if constexpr (TMEM_IO) {
                 // the next tile's stage 0 writes this buffer as soon as a warp gets there: everyone must have read first
-                cta_sync<NT, SEP>();
+                if (p.sched & 2) {
+                    __syncwarp();
+                    if ((tid & 31) == 0) mbar_arrive(bar + 80);
+                } else {
+                    cta_sync<NT, SEP>();
+                }
             } else if constexpr (TMA_IN) {
                 // this warp's share of the tile now lives in registers; when all warps have said so the producer
                 // hands the buffer to the TMA unit for the next tile
@@ -1179,7 +1312,7 @@ __global__ void __launch_bounds__(NT + ((TMA_IN && NT >= kSepProducerMinThreads)
             if constexpr (TMEM_IO) {
                 // park the results in TMEM-OUT (same lane / column-group geometry as the input side); the helper
                 // warpgroup drains them to HBM while this CTA already transforms the next tile
-                if (tile_it >= 1) mbar_wait(bar + 24, (tile_it - 1) & 1);   // previous tile's results have been drained
+                if (tile_it >= 1 && !(p.sched & 8)) mbar_wait(bar + 24, (tile_it - 1) & 1);   // previous tile's results have been drained
                 tc_fence_after();
                 int col, u;
                 map0(0, col, u);

@@ -142,10 +142,17 @@ int spectre_mix_set_tmem(int enable);
 /* Enable (default) / disable the two-pass path for n_fft > 4096 (falls back to the single-kernel variants). */
 int spectre_mix_set_two_pass(int enable);
 
-/* Experiment: hold back half of the warps by `ns` nanoseconds before the warp-local passes (0 = off). */
-int spectre_mix_set_skew_ns(int ns);
+/* Warp stagger before the warp-local passes: 0 = off; code > 0: hold back half of the warps by `code` nanoseconds;
+ * code < 0: hold back the warps of scheduler slot s by s * (|code| % 100000) clock cycles (|code| / 100000 picks the
+ * grouping: 0 four steps, 1 slots {0,1} vs {2,3}, 2 even vs odd). */
+int spectre_mix_set_skew_ns(int code);
 
-/* Debug: device buffer of grid * 8 tiles * 8 uint64 that receives per-phase %globaltimer stamps (NULL = off). */
+/* Scheduling flags of the n_fft = 4096 kernel: bit 0 stagger also before the last inverse pass; bit 1 split barrier
+ * around the last inverse pass's shared-memory read. */
+int spectre_mix_set_sched(int flags);
+
+/* Debug: device buffer of grid * 4 thread groups * 8 tiles * 8 uint64 that receives per-phase %globaltimer stamps
+ * (NULL = off). */
 int spectre_mix_set_timeline(void *device_buffer);
 
 #ifdef __cplusplus

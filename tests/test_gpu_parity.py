@@ -208,14 +208,20 @@ def test_tma_and_direct_load_paths_agree(fb, oracle, dev):
             y1 = fb.spectral_mix(*args, n_fft=n_fft, group_width=dg)
             lib.spectre_mix_set_prefetch(1)
             y2 = fb.spectral_mix(*args, n_fft=n_fft, group_width=dg)
-            lib.spectre_mix_set_prefetch(0)
             lib.spectre_mix_set_tmem(1)          # tile I/O staged through tensor memory where a variant exists (4096 fp32)
             y3 = fb.spectral_mix(*args, n_fft=n_fft, group_width=dg)
+            lib.spectre_mix_set_prefetch(0)
+            lib.spectre_mix_set_skew_ns(0)       # no warp stagger, plain CTA barrier around the last pass's read
+            lib.spectre_mix_set_sched(0)
+            y4 = fb.spectral_mix(*args, n_fft=n_fft, group_width=dg)
         finally:
             lib.spectre_mix_set_tma(1)
             lib.spectre_mix_set_tmem(1)
-            lib.spectre_mix_set_prefetch(1)
-        assert torch.equal(y0, y1) and torch.equal(y1, y2) and torch.equal(y1, y3)
+            lib.spectre_mix_set_prefetch(0)
+            lib.spectre_mix_set_skew_ns(-300)
+            lib.spectre_mix_set_sched(3)
+        y5 = fb.spectral_mix(*args, n_fft=n_fft, group_width=dg)   # defaults again
+        assert torch.equal(y0, y1) and torch.equal(y1, y2) and torch.equal(y1, y3) and torch.equal(y1, y4) and torch.equal(y1, y5)
         _check(y1, oracle.mix_flat(V, gate, n_fft, dg, mem).numpy())
 
 

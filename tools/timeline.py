@@ -20,11 +20,15 @@ ap.add_argument("--batch", type=int, default=32)
 ap.add_argument("--prefetch", type=int, default=1)
 ap.add_argument("--tma", type=int, default=1)
 ap.add_argument("--tmem", type=int, default=1)
+ap.add_argument("--skew", type=int, default=0)
+ap.add_argument("--sched", type=int, default=0)
 a = ap.parse_args()
 lib = _lib.load()
 lib.spectre_mix_set_prefetch(a.prefetch)
 lib.spectre_mix_set_tma(a.tma)
 lib.spectre_mix_set_tmem(a.tmem)
+lib.spectre_mix_set_skew_ns(a.skew)
+lib.spectre_mix_set_sched(a.sched)
 dev = torch.device("cuda")
 C, dg = 768, 16
 V = torch.randn(a.batch, a.n_fft, C, device=dev)
@@ -33,21 +37,28 @@ for _ in range(2):
     fft_b200.spectral_mix(V, g, n_fft=a.n_fft, group_width=dg)
 info = fft_b200.plan_info(a.batch, a.n_fft, a.n_fft, C, dg)
 grid = info["grid"]
-tl = torch.zeros(grid * 8 * 8, dtype=torch.int64, device=dev)
+tl = torch.zeros(grid * 4 * 8 * 8, dtype=torch.int64, device=dev)
 lib.spectre_mix_set_timeline(tl.data_ptr())
 fft_b200.spectral_mix(V, g, n_fft=a.n_fft, group_width=dg)
 torch.cuda.synchronize()
 lib.spectre_mix_set_timeline(None)
-t = tl.view(grid, 8, 8).cpu().double()
+lib.spectre_mix_set_skew_ns(0)
+lib.spectre_mix_set_sched(0)
+tall = tl.view(grid, 4, 8, 8).cpu().double()
 names = ["wait landing", "F0", "inner fwd", "MID", "inner inv", "I0 math", "output"]
-print(f"n_fft={a.n_fft} B={a.batch} grid={grid} plan={info}")
-for tile in range(1, 6):
-    d = (t[:, tile, 1:] - t[:, tile, :-1])
-    ok = t[:, tile, 7] > 0
-    if ok.sum() == 0:
-        break
-    d = d[ok]
-    tot = (t[ok, tile, 7] - t[ok, tile, 0])
-    gap = (t[ok, tile, 0] - t[ok, tile - 1, 7])
-    print(f"tile#{tile}: total {tot.mean():7.0f} ns (min {tot.min():.0f} max {tot.max():.0f})  gap-from-prev {gap.mean():5.0f} | " +
-          "  ".join(f"{n} {d[:, i].mean():6.0f}" for i, n in enumerate(names)))
+print(f"n_fft={a.n_fft} B={a.batch} grid={grid} skew={a.skew} sched={a.sched} prefetch={a.prefetch} plan={info}")
+for grp in range(4):
+    t = tall[:, grp]
+    if (t[:, 1, 7] > 0).sum() == 0:
+        continue
+    print(f"-- thread group {grp} (threads {128 * grp}..{128 * grp + 127}); stamps relative to group 0's tile start")
+    for tile in range(1, 5):
+        ok = (t[:, tile, 7] > 0) & (tall[:, 0, tile, 0] > 0)
+        if ok.sum() == 0:
+            break
+        d = (t[:, tile, 1:] - t[:, tile, :-1])[ok]
+        tot = (t[ok, tile, 7] - t[ok, tile, 0])
+        gap = (t[ok, tile, 0] - t[ok, tile - 1, 7])
+        rel = (t[ok, tile, :] - tall[ok, 0, tile, 0:1]).mean(0)
+        print(f"tile#{tile}: total {tot.mean():7.0f} ns  gap-from-prev {gap.mean():5.0f} | " +
+              "  ".join(f"{n} {d[:, i].mean():6.0f}" for i, n in enumerate(names)) + " | at " + " ".join(f"{x:6.0f}" for x in rel))
