@@ -278,7 +278,7 @@ def main():
     e2e_value = Be * SEQ * world * args.e2e_steps / float(te.item())
     e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(hV.numel() * 4 + hg.numel() * 8),
            "d2h_bytes_per_step": int(ho.numel() * 4), "batch_per_gpu": Be, "steps": args.e2e_steps,
-           "entry": "spectre_mix_fwd_host (C ABI, pinned host buffers, chunked H2D/kernel/D2H on 2 streams)"}
+           "entry": "spectre_mix_fwd_host (C ABI, pinned host buffers, chunked H2D/kernel/D2H on 4 streams)"}
 
     # ---- CPU baseline beside it (rank 0 at N=1 only)
     cpu = None

@@ -34,6 +34,7 @@ SYMBOLS = (
     "spectre_mix_set_tmem",
     "spectre_mix_set_skew_ns",
     "spectre_mix_set_sched",
+    "spectre_mix_set_l2_promotion",
     "spectre_mix_set_two_pass",
 )
 
@@ -102,6 +103,8 @@ def load():
         lib.spectre_mix_set_two_pass.argtypes = [i32]
         lib.spectre_mix_set_skew_ns.restype = i32
         lib.spectre_mix_set_skew_ns.argtypes = [i32]
+        lib.spectre_mix_set_l2_promotion.restype = i32
+        lib.spectre_mix_set_l2_promotion.argtypes = [i32]
         lib.spectre_mix_set_sched.restype = i32
         lib.spectre_mix_set_sched.argtypes = [i32]
         lib.spectre_mix_set_tmem.restype = i32

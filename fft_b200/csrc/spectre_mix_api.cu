@@ -48,6 +48,7 @@ int g_use_tmem = 1;
 int g_skew_ns = -300;   // warp stagger after the CTA barriers (see stagger() in the kernel header)
 int g_sched = 3;          // bit 0 stagger before the last inverse pass too, bit 1 split barrier around its read
 int g_use_two_pass = 1;
+int g_l2_promo = 0;       // L2 promotion of the input tensor map: 0 none, 1 64 B, 2 128 B, 3 256 B
 unsigned long long *g_timeline = nullptr;
 
 // ---------------------------------------------------------------- kernel registry
@@ -89,8 +90,12 @@ std::vector<float2> build_twiddles(const int radix[4]) {
     int P = 1;
     for (int s = 0; s < ns - 1; ++s) {
         const int R = radix[s], L = N / (P * R);
-        for (int q = 1; q < R; ++q)
+        // radix-16 stages keep rows q = 1, 2, 3, 4, 8, 12 only (spx::tw_rows): the kernel multiplies the others together
+        static const int rows16[6] = {1, 2, 3, 4, 8, 12};
+        const int nrows = spx::tw_rows(R);
+        for (int j = 0; j < nrows; ++j)
             for (int u = 0; u < L; ++u) {
+                const int q = (R == 16) ? rows16[j] : j + 1;
                 // exponent reduced modulo the period before scaling keeps the angle exact in double
                 const long long period = N / P;
                 const long long e = ((long long)u * q) % period;
@@ -251,7 +256,7 @@ bool tma_layout_ok(const void *v, int dtype, long long v_sb, long long v_sn) {
 }
 
 bool make_v_tensor_map(CUtensorMap *tm, const void *v, int dtype, long long v_sb, long long v_sn, int B, int rows, int C,
-                       int box_rows, int tile_channels) {
+                       int box_rows, int tile_channels, int l2_promo = 0) {
     EncodeTiledFn enc = encode_tiled_fn();
     if (!enc) return false;
     const cuuint64_t es = dtype == SPECTRE_MIX_F32 ? 4 : 2;
@@ -261,7 +266,11 @@ bool make_v_tensor_map(CUtensorMap *tm, const void *v, int dtype, long long v_sb
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = enc(tm, dtype == SPECTRE_MIX_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3,
                      const_cast<void *>(v), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                     CU_TENSOR_MAP_SWIZZLE_NONE,
+                     l2_promo == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
+                                   : (l2_promo == 2 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B
+                                                    : (l2_promo == 3 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_NONE)),
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS;
 }
 
@@ -324,7 +333,7 @@ int mix_two_pass(DeviceState &st, const KernelEntry &k, const void *v, int dtype
     c.gate_tables = 2;
     alignas(64) CUtensorMap tmap, tmap_out;
     bool tma = g_use_tma && k.tma_ok && (int)k.smem_bytes(2, true, false) <= st.max_smem_optin &&
-               make_v_tensor_map(&tmap, scr, SPECTRE_MIX_F32, p.v_sb, p.v_sn, B * R, sub, C, spx::kTmaBoxRows, tile_ch) &&
+               make_v_tensor_map(&tmap, scr, SPECTRE_MIX_F32, p.v_sb, p.v_sn, B * R, sub, C, spx::kTmaBoxRows, tile_ch, g_l2_promo) &&
                make_v_tensor_map(&tmap_out, scr, SPECTRE_MIX_F32, p.o_sb, p.o_sn, B * R, sub, C, k.out_box_rows, tile_ch);
     const bool tmem = tma && g_use_tmem && k.tmem_ok && (int)k.smem_bytes(2, true, true) <= st.max_smem_optin;
     if (!tma && (int)k.smem_bytes(2, false, false) > st.max_smem_optin)
@@ -370,6 +379,11 @@ int spectre_mix_set_two_pass(int enable) {
 
 int spectre_mix_set_skew_ns(int code) {
     g_skew_ns = code;
+    return 0;
+}
+
+int spectre_mix_set_l2_promotion(int level) {
+    g_l2_promo = level < 0 ? 0 : (level > 3 ? 3 : level);
     return 0;
 }
 
@@ -453,7 +467,7 @@ int spectre_mix_fwd(const void *v, int v_dtype, int64_t v_stride_b, int64_t v_st
     bool tma = g_use_tma && c.k->tma_ok && (int)c.k->smem_bytes(c.gate_tables, true, false) <= st->max_smem_optin &&
                tma_layout_ok(v, v_dtype, v_stride_b, v_stride_n) && tma_layout_ok(out, out_dtype, out_stride_b, out_stride_n) &&
                make_v_tensor_map(&tmap, v, v_dtype, v_stride_b, v_stride_n, B, n_io, C, std::min(n_fft, spx::kTmaBoxRows),
-                                 tile_ch) &&
+                                 tile_ch, g_l2_promo) &&
                make_v_tensor_map(&tmap_out, out, out_dtype, out_stride_b, out_stride_n, B, n_io, C, c.k->out_box_rows, tile_ch);
     const bool tmem = tma && g_use_tmem && c.k->tmem_ok && (int)c.k->smem_bytes(c.gate_tables, true, true) <= st->max_smem_optin;
     const int occ = std::max(1, occupancy_of(*st, c, mem != nullptr, tma, tmem));
@@ -537,9 +551,10 @@ int spectre_rfft_fwd(const void *v, int v_dtype, int64_t v_stride_b, int64_t v_s
 
 // ---------------------------------------------------------------- host-buffer entry point
 namespace {
+constexpr int kHostStreams = 4;   // chunks in flight: H2D of one, kernel of another and D2H of a third overlap, one spare
 struct HostCtx {
-    cudaStream_t s[2] = {nullptr, nullptr};
-    void *dv[2] = {nullptr, nullptr}, *dg[2] = {nullptr, nullptr}, *dout[2] = {nullptr, nullptr};
+    cudaStream_t s[kHostStreams] = {};
+    void *dv[kHostStreams] = {}, *dg[kHostStreams] = {}, *dout[kHostStreams] = {};
     size_t cap_v = 0, cap_g = 0;
     void *dmem = nullptr;
     size_t cap_mem = 0;
@@ -564,15 +579,16 @@ int spectre_mix_fwd_host(const float *v, const float *gate, const float *mem, fl
     HostCtx &h = g_host[dev];
     const size_t fh = n_fft / 2 + 1, ng = C / group_width;
     const size_t row_v = (size_t)N * C * 4, row_o = (size_t)n_io * C * 4, row_g = ng * fh * 8;
-    // batch rows per chunk: ~48 MB of V per chunk keeps both copy engines and the SMs busy
-    const int rows = (int)std::max<size_t>(1, std::min<size_t>((size_t)B, (48u << 20) / std::max<size_t>(row_v, 1)));
+    // batch rows per chunk: ~16 MB of V per chunk -- the call is PCIe-bound, so short chunks (a short pipeline fill before
+    // both copy engines run and a short drain after) matter more than filling every SM with one launch
+    const int rows = (int)std::max<size_t>(1, std::min<size_t>((size_t)B, (16u << 20) / std::max<size_t>(row_v, 1)));
     const size_t need_v = std::max(row_v, row_o) * rows, need_g = row_g * rows;
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < kHostStreams; ++i) {
         if (!h.s[i] && (e = cudaStreamCreateWithFlags(&h.s[i], cudaStreamNonBlocking)) != cudaSuccess)
             return cuda_fail(e, "cudaStreamCreate");
     }
     if (need_v > h.cap_v) {
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < kHostStreams; ++i) {
             cudaFree(h.dv[i]);
             cudaFree(h.dout[i]);
             if ((e = cudaMalloc(&h.dv[i], need_v)) != cudaSuccess) return cuda_fail(e, "cudaMalloc(V chunk)");
@@ -581,7 +597,7 @@ int spectre_mix_fwd_host(const float *v, const float *gate, const float *mem, fl
         h.cap_v = need_v;
     }
     if (need_g > h.cap_g) {
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < kHostStreams; ++i) {
             cudaFree(h.dg[i]);
             if ((e = cudaMalloc(&h.dg[i], need_g)) != cudaSuccess) return cuda_fail(e, "cudaMalloc(gate chunk)");
         }
@@ -601,7 +617,7 @@ int spectre_mix_fwd_host(const float *v, const float *gate, const float *mem, fl
     int chunk = 0;
     for (int b0 = 0; b0 < B; b0 += rows, ++chunk) {
         const int nb = std::min(rows, B - b0);
-        const int i = chunk & 1;
+        const int i = chunk % kHostStreams;
         cudaStream_t s = h.s[i];
         if ((e = cudaMemcpyAsync(h.dv[i], v + (size_t)b0 * N * C, row_v * nb, cudaMemcpyHostToDevice, s)) != cudaSuccess)
             return cuda_fail(e, "H2D V");
@@ -615,7 +631,7 @@ int spectre_mix_fwd_host(const float *v, const float *gate, const float *mem, fl
             cudaSuccess)
             return cuda_fail(e, "D2H out");
     }
-    for (int i = 0; i < 2; ++i)
+    for (int i = 0; i < kHostStreams; ++i)
         if ((e = cudaStreamSynchronize(h.s[i])) != cudaSuccess) return cuda_fail(e, "stream sync");
     return 0;
 }

@@ -64,6 +64,7 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
     return t;
 }
 constexpr int kTimelineSlots = 8;     // timestamps per tile
+constexpr int kTimelineGroups = 5;    // four compute thread groups + the helper warpgroup's elected thread
 constexpr int kTimelineTiles = 8;     // tiles recorded per CTA (by thread 0 of each of the up to four 128-thread groups)
 
 // ------------------------------------------------------------------ packed / scalar lanes
@@ -193,6 +194,11 @@ struct Dft<16, V> {
 // SUBP: this transform is one of R interleaved sub-transforms of a longer one (n_total = R * N, first radix-R
 // stage and its twiddles done by the pre/post pass kernels of the long-context path): the input is already complex,
 // the gate is gathered with stride R and is not Hermitian within the sub-spectrum.
+// Twiddle rows kept per stage.  A radix-16 stage stores only q in {1, 2, 3, 4, 8, 12} (rows 0..5): W^{u (q1 + 4 q0)} =
+// W^{u q1} W^{4 u q0}, so six loads and nine scalar complex products replace fifteen loads -- 40 % of the table, which is
+// what lets the stage-0 table of the 4096-point plan shrink from 30 KB to 12 KB of shared memory.
+__host__ __device__ constexpr int tw_rows(int R) { return R == 16 ? 6 : R - 1; }
+
 template <int R0, int R1, int R2, int R3, bool SUBP = false>
 struct Plan {
     static constexpr bool kSub = SUBP;
@@ -202,8 +208,8 @@ struct Plan {
     __host__ __device__ static constexpr int R(int s) { return s == 0 ? R0 : (s == 1 ? R1 : (s == 2 ? R2 : R3)); }
     __host__ __device__ static constexpr int P(int s) { return s == 0 ? 1 : (s == 1 ? R0 : (s == 2 ? R0 * R1 : R0 * R1 * R2)); }
     __host__ __device__ static constexpr int L(int s) { return N / (P(s) * R(s)); }
-    // twiddles of stage s (s < NS-1): W_{N/P}^{u q}, stored at TWOFF(s) + (q-1) L + u
-    __host__ __device__ static constexpr int TWOFF(int s) { return s == 0 ? 0 : TWOFF(s - 1) + (R(s - 1) - 1) * L(s - 1); }
+    // twiddles of stage s (s < NS-1): W_{N/P}^{u q}, row j of the stage's table at TWOFF(s) + j L + u (see tw_rows)
+    __host__ __device__ static constexpr int TWOFF(int s) { return s == 0 ? 0 : TWOFF(s - 1) + tw_rows(R(s - 1)) * L(s - 1); }
     static constexpr int TWN = TWOFF(NS - 1);
     static constexpr int NPAD = N + (N >> 4);
     static constexpr int GPAD = (N / 2) + ((N / 2) >> 4) + 1;  // padded gate table length (float2)
@@ -212,8 +218,11 @@ struct Plan {
 __host__ __device__ constexpr int cmax(int a, int b) { return a > b ? a : b; }
 // ring of TMA boxes shared by both directions of the TMEM variant: while a tile is parked all but one slot hold
 // loads in flight (latency cover), while results are drained all of them are store sources
-constexpr int kTmemSlots = 5;
+constexpr int kTmemSlots = 7;
 // register split of the TMEM variant (512 compute + 128 helper threads, 96 per thread at launch = 61440 in the CTA pool)
+#ifndef SPX_HELPER_TL
+#define SPX_HELPER_TL 0
+#endif
 #ifndef SPX_COOP_PF
 #define SPX_COOP_PF 0
 #endif
@@ -224,6 +233,7 @@ constexpr int kTmemSlots = 5;
 #define SPX_TMEM_COMPUTE_REGS 112
 #endif
 constexpr int kTmemComputeRegs = SPX_TMEM_COMPUTE_REGS, kTmemHelperRegs = (96 * 640 - SPX_TMEM_COMPUTE_REGS * 512) / 128;
+static_assert(32 + 8 * kTmemSlots <= 96, "ring barriers overlap the TMEM base slot");
 static_assert(kTmemHelperRegs % 8 == 0 && kTmemHelperRegs >= 24, "setmaxnreg takes multiples of 8");
 
 // Which stages keep their twiddles in shared memory: all of them while the tables fit beside the tile; from
@@ -237,6 +247,38 @@ template <class PL, int S_>
 __device__ __forceinline__ float2 tw_get(const float2 *tw_s, const float2 *tw_g, int idx) {
     if constexpr (S_ >= TwPolicy<PL>::FROM) return tw_s[PL::TWOFF(S_) - PL::TWOFF(TwPolicy<PL>::FROM) + idx];
     else return __ldg(tw_g + PL::TWOFF(S_) + idx);
+}
+
+// x[q] *= W^{u q}, q = 1 .. R-1, for stage S_ (forward sign; the inverse passes call it on (im, re)-swapped data)
+template <class PL, int S_, class V>
+__device__ __forceinline__ void apply_twiddles(Cx<V> (&x)[PL::R(S_)], const float2 *tw_s, const float2 *tw_g, int u) {
+    constexpr int R = PL::R(S_), L = PL::L(S_);
+    if constexpr (R == 16) {
+        float2 a[4], b[4];   // a[q1] = W^{u q1}, b[q0] = W^{4 u q0}
+#pragma unroll
+        for (int j = 1; j < 4; ++j) {
+            a[j] = tw_get<PL, S_>(tw_s, tw_g, (j - 1) * L + u);
+            b[j] = tw_get<PL, S_>(tw_s, tw_g, (j + 2) * L + u);
+        }
+#pragma unroll
+        for (int q0 = 0; q0 < 4; ++q0)
+#pragma unroll
+            for (int q1 = 0; q1 < 4; ++q1) {
+                const int q = q1 + 4 * q0;
+                if (q == 0) continue;
+                float2 w;
+                if (q0 == 0) w = a[q1];
+                else if (q1 == 0) w = b[q0];
+                else w = make_float2(fmaf(-a[q1].y, b[q0].y, a[q1].x * b[q0].x), fmaf(a[q1].x, b[q0].y, a[q1].y * b[q0].x));
+                x[q] = cmul(x[q], w.x, w.y);
+            }
+    } else {
+#pragma unroll
+        for (int q = 1; q < R; ++q) {
+            const float2 wq = tw_get<PL, S_>(tw_s, tw_g, (q - 1) * L + u);
+            x[q] = cmul(x[q], wq.x, wq.y);
+        }
+    }
 }
 
 // ------------------------------------------------------------------ element traits per mode
@@ -392,11 +434,7 @@ __device__ __forceinline__ void fwd_inner_pass(typename Elem<MODE>::S *buf, cons
 #pragma unroll
         for (int m = 0; m < R; ++m) x[m] = E::unpack(cb[m * L + ((m * L) >> 4)]);
         Dft<R, V>::run(x);
-#pragma unroll
-        for (int q = 1; q < R; ++q) {
-            const float2 wq = tw_get<PL, S_>(tw, twg, (q - 1) * L + u);
-            x[q] = cmul(x[q], wq.x, wq.y);
-        }
+        apply_twiddles<PL, S_, V>(x, tw, twg, u);
 #pragma unroll
         for (int q = 0; q < R; ++q) cb[q * L + ((q * L) >> 4)] = E::pack(x[q]);
     }
@@ -416,13 +454,8 @@ __device__ __forceinline__ void inv_inner_pass(typename Elem<MODE>::S *buf, cons
         typename E::S *cb = buf + col * CS + e0 + (e0 >> 4);
         Cx<V> x[R];
 #pragma unroll
-        for (int q = 0; q < R; ++q) {
-            x[q] = cswap(E::unpack(cb[q * L + ((q * L) >> 4)]));
-            if (q > 0) {
-                const float2 wq = tw_get<PL, S_>(tw, twg, (q - 1) * L + u);
-                x[q] = cmul(x[q], wq.x, wq.y);
-            }
-        }
+        for (int q = 0; q < R; ++q) x[q] = cswap(E::unpack(cb[q * L + ((q * L) >> 4)]));
+        apply_twiddles<PL, S_, V>(x, tw, twg, u);
         Dft<R, V>::run(x);
 #pragma unroll
         for (int m = 0; m < R; ++m) cb[m * L + ((m * L) >> 4)] = E::pack(cswap(x[m]));
@@ -794,7 +827,8 @@ __global__ void __launch_bounds__(NT + ((TMA_IN && NT >= kSepProducerMinThreads)
     }
     // ---------------------------------------------------------------- TMEM-staged variant: set-up + helper warpgroup
     // barriers:  +0 tile parked in TMEM-IN (helper)   +8 TMEM-IN consumed (NW warps)   +16 results parked in TMEM-OUT (NW warps)
-    //            +24 TMEM-OUT drained (helper)   +32.. ring slot landed (TMA tx, kTmemSlots of them)   +96 TMEM base address
+    //            +24 TMEM-OUT drained (helper)   +32.. ring slot landed (TMA tx, kTmemSlots of them, < +96)   +96 TMEM base address
+    //            +104 twiddle table landed   +112 last inverse pass has read the buffer (NW warps, split barrier)
     // ring (the staging area): kTmemSlots slots of one 256-row TMA box each, used for loads while parking and for
     // stores while draining
     [[maybe_unused]] uint32_t tmem_base = 0;
@@ -808,7 +842,7 @@ __global__ void __launch_bounds__(NT + ((TMA_IN && NT >= kSepProducerMinThreads)
             mbar_init(bar_in_free, NW);
             mbar_init(bar_out_full, NW);
             mbar_init(bar_out_free, 1);
-            mbar_init(bar + 80, NW);                                  // inverse stage-0 read done (split barrier, sched bit 1)
+            mbar_init(bar + 112, NW);                                  // inverse stage-0 read done (split barrier, sched bit 1)
 #pragma unroll
             for (int i = 0; i < kTmemSlots; ++i) mbar_init(bar_landed + 8 * i, 1);
         }
@@ -872,10 +906,21 @@ __global__ void __launch_bounds__(NT + ((TMA_IN && NT >= kSepProducerMinThreads)
 #pragma unroll 1
             for (int P = 0; P < phases; ++P) {
                 const bool do_park = P < my_tiles, do_drain = P >= 2;
+#if SPX_HELPER_TL
+                // diagnostic build: the elected thread records, per phase, entry / start / end stamps (ns) and the cycles it
+                // spent waiting for landings, moving data, at the helper barrier and in its TMA duties
+                const bool tl_on = p.timeline && hl == 0 && P < kTimelineTiles;
+                unsigned long long *tl = p.timeline + (((size_t)blockIdx.x * kTimelineGroups + 4) * kTimelineTiles + (P < kTimelineTiles ? P : 0)) * kTimelineSlots;
+                long long c_land = 0, c_move = 0, c_bar = 0, c_tma = 0;
+                if (tl_on) tl[0] = globaltimer_ns();
+#endif
                 if (do_park && P >= 1) mbar_wait(bar_in_free, (P - 1) & 1);    // compute warps pulled tile P-1 out of TMEM-IN
                 if (do_drain) mbar_wait(bar_out_full, (P - 2) & 1);            // results of tile P-2 sit in TMEM-OUT
                 tc_fence_after();
                 if (p.prefetch == 1 && hl == 0 && P + 2 < my_tiles) prefetch_tile((int)blockIdx.x + (P + 2) * (int)gridDim.x);
+#if SPX_HELPER_TL
+                if (tl_on) tl[1] = globaltimer_ns();
+#endif
                 const int td = (int)blockIdx.x + (P - 2) * (int)gridDim.x;
                 const int tb = do_drain ? td / p.tiles_per_row : 0;
                 const int tc = do_drain ? (td - tb * p.tiles_per_row) * NCOL * CH : 0;
@@ -898,9 +943,15 @@ __global__ void __launch_bounds__(NT + ((TMA_IN && NT >= kSepProducerMinThreads)
                         pf += (long long)kTmaBoxRows * p.v_sn;
                     }
 #endif
+#if SPX_HELPER_TL
+                    long long c0 = clock64(), c1 = c0;
+#endif
                     if (do_park) {
                         mbar_wait(bar_landed + 8 * sl, (landed_par >> sl) & 1);
                         landed_par ^= 1u << sl;
+#if SPX_HELPER_TL
+                        c1 = clock64();
+#endif
 #pragma unroll
                         for (int g = 0; g < GPB; ++g) v[g] = slot[g * 128 + hl];      // consecutive lanes, consecutive slots
 #pragma unroll
@@ -915,7 +966,13 @@ __global__ void __launch_bounds__(NT + ((TMA_IN && NT >= kSepProducerMinThreads)
                         for (int g = 0; g < GPB; ++g) slot[g * 128 + hl] = v[g];
                         fence_proxy_async();
                     }
+#if SPX_HELPER_TL
+                    const long long c2 = clock64();
+#endif
                     helper_bar();                                  // slot read by all (park) / written by all (drain)
+#if SPX_HELPER_TL
+                    const long long c3 = clock64();
+#endif
                     if (hl == 0) {
                         if (do_drain) {
                             tma_store_3d(&tmap_out, smem_u32(slot), tc, k * kTmaBoxRows, tb);
@@ -924,8 +981,14 @@ __global__ void __launch_bounds__(NT + ((TMA_IN && NT >= kSepProducerMinThreads)
                         }
                         if (ld_left > 0) issue_next();             // ... which is where the next load of the stream lands
                     }
+#if SPX_HELPER_TL
+                    c_land += c1 - c0; c_move += c2 - c1; c_bar += c3 - c2; c_tma += clock64() - c3;
+#endif
                     sl = (sl + 1 == kTmemSlots) ? 0 : sl + 1;
                 }
+#if SPX_HELPER_TL
+                if (tl_on) { tl[2] = globaltimer_ns(); tl[3] = c_land; tl[4] = c_move; tl[5] = c_bar; tl[6] = c_tma; }
+#endif
                 if (do_park) tmem_wait_st();
                 tc_fence_before();
                 helper_bar();
@@ -975,7 +1038,7 @@ __global__ void __launch_bounds__(NT + ((TMA_IN && NT >= kSepProducerMinThreads)
     int tl_tile = 0;
 #define SPX_MARK(slot)                                                                                   \
     if (p.timeline && (tid & 127) == 0 && tl_tile < kTimelineTiles)                                      \
-        p.timeline[(((size_t)blockIdx.x * 4 + (tid >> 7)) * kTimelineTiles + tl_tile) * kTimelineSlots + (slot)] = globaltimer_ns();
+        p.timeline[(((size_t)blockIdx.x * kTimelineGroups + (tid >> 7)) * kTimelineTiles + tl_tile) * kTimelineSlots + (slot)] = globaltimer_ns();
     uint32_t rnd = 0;   // output staging rounds issued so far (buffer = rnd & 1)
     // stage-0 butterfly of (thread, iteration): channel column and row offset u.  The TMEM variant ties u to the TMEM lane
     // the thread can reach: lane = 32 * (warp % 4) + lane id = u mod 128.
@@ -1113,14 +1176,10 @@ __global__ void __launch_bounds__(NT + ((TMA_IN && NT >= kSepProducerMinThreads)
                 map0(it, col, u);
                 if (ITEMS0 % NT == 0 || w < ITEMS0) {
                     Dft<R0, V>::run(x0[it]);
-#pragma unroll
-                    for (int q = 1; q < R0; ++q) {
-                        const float2 wq = tw_get<PL, 0>(tw, p.tw, (q - 1) * L0 + u);
-                        x0[it][q] = cmul(x0[it][q], wq.x, wq.y);
-                    }
+                    apply_twiddles<PL, 0, V>(x0[it], tw, p.tw, u);
                     if constexpr (TMEM_IO) {
                         // split barrier: every warp has pulled the previous tile's last pass out of the buffer
-                        if ((p.sched & 2) && tile_it >= 1) mbar_wait(bar + 80, (tile_it - 1) & 1);
+                        if ((p.sched & 2) && tile_it >= 1) mbar_wait(bar + 112, (tile_it - 1) & 1);
                     }
                     S *cb = buf + col * CS + u + (u >> 4);
 #pragma unroll
@@ -1278,7 +1337,7 @@ __global__ void __launch_bounds__(NT + ((TMA_IN && NT >= kSepProducerMinThreads)
                 // the next tile's stage 0 writes this buffer as soon as a warp gets there: everyone must have read first
                 if (p.sched & 2) {
                     __syncwarp();
-                    if ((tid & 31) == 0) mbar_arrive(bar + 80);
+                    if ((tid & 31) == 0) mbar_arrive(bar + 112);
                 } else {
                     cta_sync<NT, SEP>();
                 }
@@ -1300,11 +1359,7 @@ __global__ void __launch_bounds__(NT + ((TMA_IN && NT >= kSepProducerMinThreads)
                 map0(it, col, u);
                 (void)col;
                 if (ITEMS0 % NT == 0 || w < ITEMS0) {
-#pragma unroll
-                    for (int q = 1; q < R0; ++q) {
-                        const float2 wq = tw_get<PL, 0>(tw, p.tw, (q - 1) * L0 + u);
-                        x0[it][q] = cmul(x0[it][q], wq.x, wq.y);
-                    }
+                    apply_twiddles<PL, 0, V>(x0[it], tw, p.tw, u);
                     Dft<R0, V>::run(x0[it]);
                 }
             }

@@ -147,6 +147,9 @@ int spectre_mix_set_two_pass(int enable);
  * grouping: 0 four steps, 1 slots {0,1} vs {2,3}, 2 even vs odd). */
 int spectre_mix_set_skew_ns(int code);
 
+/* L2 promotion of the input tensor map (TMA loads): 0 none (default), 1 = 64 B, 2 = 128 B, 3 = 256 B.  For experiments. */
+int spectre_mix_set_l2_promotion(int level);
+
 /* Scheduling flags of the n_fft = 4096 kernel: bit 0 stagger also before the last inverse pass; bit 1 split barrier
  * around the last inverse pass's shared-memory read. */
 int spectre_mix_set_sched(int flags);
