@@ -82,6 +82,14 @@ struct DeviceState {
 std::mutex g_mu;
 std::map<int, DeviceState> g_dev;
 
+// log2(x) when x is a power of two, else -1
+int ilog2_exact(int x) {
+    if (x <= 0 || (x & (x - 1))) return -1;
+    int s = 0;
+    while ((1 << s) < x) ++s;
+    return s;
+}
+
 // W_{N/P(s)}^{u q} for every non-final stage, laid out exactly as Plan::TWOFF expects.
 std::vector<float2> build_twiddles(const int radix[4]) {
     int N = radix[0] * radix[1] * radix[2] * radix[3];
@@ -328,6 +336,8 @@ int mix_two_pass(DeviceState &st, const KernelEntry &k, const void *v, int dtype
     p.skew_ns = g_skew_ns;
     p.sched = g_sched;
     p.sub_R = R;
+    p.sub_shift = ilog2_exact(R);
+    p.gw_shift = ilog2_exact(group_width);
     Choice c;
     c.k = &k;
     c.gate_tables = 2;
@@ -460,6 +470,8 @@ int spectre_mix_fwd(const void *v, int v_dtype, int64_t v_stride_b, int64_t v_st
     p.skew_ns = g_skew_ns;
     p.sched = g_sched;
     p.sub_R = 1;
+    p.sub_shift = 0;
+    p.gw_shift = ilog2_exact(group_width);
 
     // TMA-fed variant when V's layout can be described to the TMA unit; otherwise direct 128-bit global loads
     alignas(64) CUtensorMap tmap, tmap_out;
@@ -543,6 +555,8 @@ int spectre_rfft_fwd(const void *v, int v_dtype, int64_t v_stride_b, int64_t v_s
     p.gate_tables = 0;
     p.inv_n = 1.0f;
     p.prefetch = 0;
+    p.sub_R = 1;
+    p.gw_shift = 0;
     const int grid = std::min(p.num_tiles, st->sm_count * std::max(1, c.k->minb));
     cudaError_t e = c.k->launch_rfft(p, grid, reinterpret_cast<cudaStream_t>(stream));
     if (e != cudaSuccess) return cuda_fail(e, "rfft kernel launch");

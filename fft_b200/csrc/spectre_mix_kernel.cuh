@@ -51,6 +51,8 @@ struct MixParams {
     int gate_tables;      // gate groups a tile may touch (smem sized for this many)
     float inv_n;
     int prefetch;         // 1: prefetch the CTA's next tile into L2 while this one is transformed
+    int gw_shift;         // log2(group_width) when it is a power of two, else -1 (the kernel then divides)
+    int sub_shift;        // log2(sub_R)
     int sub_R;            // long-context path: number of interleaved sub-transforms (n_total = sub_R * n_fft), else 1
     int skew_ns;          // warp stagger code (see stagger()): 0 off, > 0 legacy nanosleep, < 0 clock spin per scheduler slot
     int sched;            // bit 0: stagger also after the barrier before inverse stage 0; bit 1 (TMEM variant): split barrier
@@ -220,6 +222,9 @@ __host__ __device__ constexpr int cmax(int a, int b) { return a > b ? a : b; }
 // loads in flight (latency cover), while results are drained all of them are store sources
 constexpr int kTmemSlots = 7;
 // register split of the TMEM variant (512 compute + 128 helper threads, 96 per thread at launch = 61440 in the CTA pool)
+#ifndef SPX_SPLIT_DUTY
+#define SPX_SPLIT_DUTY 1
+#endif
 #ifndef SPX_HELPER_TL
 #define SPX_HELPER_TL 0
 #endif
@@ -878,8 +883,9 @@ __global__ void __launch_bounds__(NT + ((TMA_IN && NT >= kSepProducerMinThreads)
                 ld_tb = ld_t / p.tiles_per_row;
                 ld_tc = (ld_t - ld_tb * p.tiles_per_row) * NCOL * CH;
             }
-            auto issue_next = [&]() {                             // elected thread: next box of the stream -> next slot
-                fence_proxy_async();
+            auto issue_next = [&]() {                             // load thread: next box of the stream -> next slot
+                // (no proxy fence: the slot was last touched by shared-memory READS of the helper threads, ordered by the
+                // helper barrier, or by a TMA store whose read the store thread has waited for)
                 mbar_expect_tx(bar_landed + 8 * ld_slot, SLOTB);
                 tma_load_3d(smem_u32(stg) + ld_slot * SLOTB, &tmap, ld_tc, ld_k * kTmaBoxRows, ld_tb, bar_landed + 8 * ld_slot);
                 --ld_left;
@@ -891,8 +897,16 @@ __global__ void __launch_bounds__(NT + ((TMA_IN && NT >= kSepProducerMinThreads)
                     ld_tc = (ld_t - ld_tb * p.tiles_per_row) * NCOL * CH;
                 }
             };
-            if (hl == 0) {
-                for (int i = 0; i < DEPTH && ld_left > 0; ++i) issue_next();
+            // two duty threads in different warps so the store and the load of a step are issued side by side: kStoreLane
+            // issues / commits / waits for the TMA stores, kLoadLane issues the loads.  The load of step j goes to the slot of the
+            // store of step j - 2, whose read the store thread awaited before it entered the barrier of step j.
+#if SPX_SPLIT_DUTY
+            constexpr int kStoreLane = 0, kLoadLane = 32, kDepth = kTmemSlots - 2;
+#else
+            constexpr int kStoreLane = 0, kLoadLane = 0, kDepth = DEPTH;
+#endif
+            if (hl == kLoadLane) {
+                for (int i = 0; i < kDepth && ld_left > 0; ++i) issue_next();
                 if (p.prefetch == 1 && my_tiles > 1) prefetch_tile((int)blockIdx.x + (int)gridDim.x);
             }
             // prefetch == 2: the four CTAs that work on four adjacent channel tiles pull the NEXT tiles' rows into L2 as whole
@@ -917,7 +931,7 @@ __global__ void __launch_bounds__(NT + ((TMA_IN && NT >= kSepProducerMinThreads)
                 if (do_park && P >= 1) mbar_wait(bar_in_free, (P - 1) & 1);    // compute warps pulled tile P-1 out of TMEM-IN
                 if (do_drain) mbar_wait(bar_out_full, (P - 2) & 1);            // results of tile P-2 sit in TMEM-OUT
                 tc_fence_after();
-                if (p.prefetch == 1 && hl == 0 && P + 2 < my_tiles) prefetch_tile((int)blockIdx.x + (P + 2) * (int)gridDim.x);
+                if (p.prefetch == 1 && hl == kLoadLane && P + 2 < my_tiles) prefetch_tile((int)blockIdx.x + (P + 2) * (int)gridDim.x);
 #if SPX_HELPER_TL
                 if (tl_on) tl[1] = globaltimer_ns();
 #endif
@@ -973,14 +987,12 @@ __global__ void __launch_bounds__(NT + ((TMA_IN && NT >= kSepProducerMinThreads)
 #if SPX_HELPER_TL
                     const long long c3 = clock64();
 #endif
-                    if (hl == 0) {
-                        if (do_drain) {
-                            tma_store_3d(&tmap_out, smem_u32(slot), tc, k * kTmaBoxRows, tb);
-                            tma_commit();
-                            tma_wait_read<SP>();                   // the store of step - SP has left its slot ...
-                        }
-                        if (ld_left > 0) issue_next();             // ... which is where the next load of the stream lands
+                    if (hl == kStoreLane && do_drain) {
+                        tma_store_3d(&tmap_out, smem_u32(slot), tc, k * kTmaBoxRows, tb);
+                        tma_commit();
+                        tma_wait_read<SP>();                       // the store of step - SP has left its slot
                     }
+                    if (hl == kLoadLane && ld_left > 0) issue_next();   // into a slot whose store is known to have been read
 #if SPX_HELPER_TL
                     c_land += c1 - c0; c_move += c2 - c1; c_bar += c3 - c2; c_tma += clock64() - c3;
 #endif
@@ -1055,13 +1067,21 @@ __global__ void __launch_bounds__(NT + ((TMA_IN && NT >= kSepProducerMinThreads)
         }
     };
 
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        const int brow = tile / p.tiles_per_row;                 // row of the [B'][n_fft][C] tensor the tile lives in
-        const int b = SUB ? brow / p.sub_R : brow;               // batch row (gate / memory)
-        const int qsub = SUB ? brow % p.sub_R : 0;               // which interleaved sub-transform
-        const int ce0 = (tile - brow * p.tiles_per_row) * NCOL;  // first element column of the tile
+    // tile -> (row of the [B'][n_fft][C] tensor, channel-tile column), advanced incrementally: integer divisions sit on every
+    // warp's serial path between two tiles, so the loop has none (group index by shift when group_width is a power of two)
+    const int step_row = (int)gridDim.x / p.tiles_per_row, step_col = (int)gridDim.x - step_row * p.tiles_per_row;
+    int brow = (int)blockIdx.x / p.tiles_per_row, tcol = (int)blockIdx.x - brow * p.tiles_per_row;
+    int nrow_ = 0, ncol_ = 0;
+    auto gdiv = [&](int x) { return p.gw_shift >= 0 ? (x >> p.gw_shift) : x / p.group_width; };
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, brow = nrow_, tcol = ncol_) {
+        nrow_ = brow + step_row;
+        ncol_ = tcol + step_col;
+        if (ncol_ >= p.tiles_per_row) { ncol_ -= p.tiles_per_row; ++nrow_; }
+        const int b = SUB ? (brow >> p.sub_shift) : brow;        // batch row (gate / memory)
+        const int qsub = SUB ? (brow & (p.sub_R - 1)) : 0;       // which interleaved sub-transform
+        const int ce0 = tcol * NCOL;                             // first element column of the tile
         const int c0 = ce0 * CH;
-        const int g0 = c0 / p.group_width;
+        const int g0 = gdiv(c0);
         const bool full_tile = (ce0 + NCOL <= CE) && (p.n_in == N);
         SPX_MARK(0)
 
@@ -1231,7 +1251,7 @@ __global__ void __launch_bounds__(NT + ((TMA_IN && NT >= kSepProducerMinThreads)
                     }
                     continue;
                 }
-                const float2 *gs = gate_s + (cabs / p.group_width - g0) * GS;
+                const float2 *gs = gate_s + (p.gate_tables == 1 ? 0 : (gdiv(cabs) - g0) * GS);
                 // bins k = klow + PLAST q (q < RL/2) use G[k]; the mirrored half uses conj(G[N - k])
                 const int plo = klow + (klow >> 4);                // padded index of bin klow
                 const int nk = N - klow;                           // N - klow - PLAST q stays >= N/2 - ... >= 1
@@ -1286,11 +1306,11 @@ __global__ void __launch_bounds__(NT + ((TMA_IN && NT >= kSepProducerMinThreads)
         const bool fetch_next = gate_early && tile_next < p.num_tiles;
         int nq = 0;
         if (fetch_next) {
-            const int nrow = tile_next / p.tiles_per_row;
-            const int ng = ((tile_next - nrow * p.tiles_per_row) * NCOL * CH) / p.group_width;
+            const int nrow = nrow_;
+            const int ng = gdiv(ncol_ * NCOL * CH);
             if constexpr (SUB) {
-                nq = nrow % p.sub_R;
-                gate_fetch_sub<N, NT, GKS>(gnext, p.gate + ((long long)(nrow / p.sub_R) * p.NG + ng) * ((N * p.sub_R) / 2 + 1), tid, nq,
+                nq = nrow & (p.sub_R - 1);
+                gate_fetch_sub<N, NT, GKS>(gnext, p.gate + ((long long)(nrow >> p.sub_shift) * p.NG + ng) * ((N * p.sub_R) / 2 + 1), tid, nq,
                                            p.sub_R);
             } else {
 #if !SPX_GATE_ASYNC
@@ -1308,8 +1328,8 @@ __global__ void __launch_bounds__(NT + ((TMA_IN && NT >= kSepProducerMinThreads)
             } else {
 #if SPX_GATE_ASYNC
                 // every warp is past the middle pass: the next tile's gate row may stream into the table
-                const int nrow = tile_next / p.tiles_per_row;
-                const int ng = ((tile_next - nrow * p.tiles_per_row) * NCOL * CH) / p.group_width;
+                const int nrow = nrow_;
+                const int ng = gdiv(ncol_ * NCOL * CH);
                 gate_copy_async<N, NT, GK>(gate_s, p.gate + ((long long)nrow * p.NG + ng) * (N / 2 + 1), tid);
 #else
                 gate_put<N, NT, GK>(gate_s, gnext, tid, p.inv_n);
