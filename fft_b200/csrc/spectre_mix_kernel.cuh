@@ -220,7 +220,10 @@ struct Plan {
 __host__ __device__ constexpr int cmax(int a, int b) { return a > b ? a : b; }
 // ring of TMA boxes shared by both directions of the TMEM variant: while a tile is parked all but one slot hold
 // loads in flight (latency cover), while results are drained all of them are store sources
-constexpr int kTmemSlots = 7;
+constexpr int kTmemSlotsMax = 7;
+// ring slots of a plan: the sub-transform variant holds a full-length gate table (two half-length slots) and has room for six
+template <class PL>
+__host__ __device__ constexpr int tmem_slots() { return PL::kSub ? 6 : kTmemSlotsMax; }
 // register split of the TMEM variant (512 compute + 128 helper threads, 96 per thread at launch = 61440 in the CTA pool)
 #ifndef SPX_SPLIT_DUTY
 #define SPX_SPLIT_DUTY 1
@@ -238,7 +241,7 @@ constexpr int kTmemSlots = 7;
 #define SPX_TMEM_COMPUTE_REGS 112
 #endif
 constexpr int kTmemComputeRegs = SPX_TMEM_COMPUTE_REGS, kTmemHelperRegs = (96 * 640 - SPX_TMEM_COMPUTE_REGS * 512) / 128;
-static_assert(32 + 8 * kTmemSlots <= 96, "ring barriers overlap the TMEM base slot");
+static_assert(32 + 8 * kTmemSlotsMax <= 96, "ring barriers overlap the TMEM base slot");
 static_assert(kTmemHelperRegs % 8 == 0 && kTmemHelperRegs >= 24, "setmaxnreg takes multiples of 8");
 
 // Which stages keep their twiddles in shared memory: all of them while the tables fit beside the tile; from
@@ -402,7 +405,7 @@ struct Smem {
     // TMEM variant: ring of kTmemSlots + kTmemStoreSlots TMA boxes (256 rows each) instead of the staging buffers
     static constexpr size_t bytes(int gate_tables, bool tma = false, size_t row_bytes = 0, bool tmem = false) {
         return ((base_bytes(gate_tables) + 127) / 128) * 128 + bar_bytes +
-               (tmem ? (size_t)kTmemSlots * 256 * row_bytes : (tma ? 2 * stg_bytes(row_bytes) : 0));
+               (tmem ? (size_t)tmem_slots<PL>() * 256 * row_bytes : (tma ? 2 * stg_bytes(row_bytes) : 0));
     }
 };
 
@@ -748,6 +751,7 @@ __global__ void __launch_bounds__(NT + ((TMA_IN && NT >= kSepProducerMinThreads)
     unsigned char *stg = smem_raw + bar_off + SM::bar_bytes;
     constexpr int NW = NT / 32;
     constexpr bool SEP = TMA_IN && (NT >= kSepProducerMinThreads);   // separate producer warpgroup
+    [[maybe_unused]] constexpr int kTmemSlots = tmem_slots<PL>();        // ring slots of the TMEM variant
     // TMEM layout of a parked tile: the tile as a flat array of elements e = row * NCOL + col (16 bytes each), element e in
     // lane e % 128, columns 4 * (e / 128) .. +3.  Helper threads then touch consecutive 16-byte slots of the ring (no bank
     // conflicts) and a compute thread finds all 16 inputs of its stage-0 butterfly in its own lane.

@@ -16,7 +16,7 @@ ap.add_argument("--batch", type=int, default=32)
 ap.add_argument("--channels", type=int, default=768)
 ap.add_argument("--group-width", type=int, default=16)
 ap.add_argument("--tile", type=int, default=0)
-ap.add_argument("--prefetch", type=int, default=1)
+ap.add_argument("--prefetch", type=int, default=0)
 ap.add_argument("--reps", type=int, default=4)
 ap.add_argument("--bf16", action="store_true")
 ap.add_argument("--mem", action="store_true")

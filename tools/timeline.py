@@ -19,7 +19,7 @@ if os.environ.get('SPX_ALT'):
 ap = argparse.ArgumentParser()
 ap.add_argument("--n-fft", type=int, default=4096)
 ap.add_argument("--batch", type=int, default=32)
-ap.add_argument("--prefetch", type=int, default=1)
+ap.add_argument("--prefetch", type=int, default=0)
 ap.add_argument("--tma", type=int, default=1)
 ap.add_argument("--tmem", type=int, default=1)
 ap.add_argument("--skew", type=int, default=0)
