@@ -45,7 +45,7 @@ int g_tile_channels_override = 0;
 int g_prefetch = 0;   // L2 prefetch of the next tiles: 0 off (default: the TMA unit is the busiest part of the TMEM variant), 1 TMA prefetch, 2 cooperative whole-line prefetch (needs -DSPX_COOP_PF=1)
 int g_use_tma = 1;
 int g_use_tmem = 1;
-int g_skew_ns = -300;   // warp stagger after the CTA barriers (see stagger() in the kernel header)
+int g_skew_ns = -350;   // warp stagger after the CTA barriers (see stagger() in the kernel header)
 int g_sched = 3;          // bit 0 stagger before the last inverse pass too, bit 1 split barrier around its read
 int g_use_two_pass = 1;
 int g_l2_promo = 0;       // L2 promotion of the input tensor map: 0 none, 1 64 B, 2 128 B, 3 256 B

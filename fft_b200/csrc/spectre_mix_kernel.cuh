@@ -1221,7 +1221,7 @@ __global__ void __launch_bounds__(NT + ((TMA_IN && NT >= kSepProducerMinThreads)
         SPX_MARK(2)
         // stagger: with every warp in lock step all of them load, then all compute, then all store; holding back two of
         // the four warps of each scheduler lets their shared-memory phases overlap the others' butterflies
-        if constexpr (TMEM_IO) stagger(p.skew_ns, tid);
+        if (TMEM_IO || (p.sched & 64)) stagger(p.skew_ns, tid);
 
         // ---- forward stages 1 .. NS-2: smem -> butterfly -> twiddle -> smem (in place)
         // The exchange between stage NS-2 and the middle pass is a 16x16 transpose among the 16 threads that share
@@ -1341,7 +1341,7 @@ __global__ void __launch_bounds__(NT + ((TMA_IN && NT >= kSepProducerMinThreads)
             }
         }
         SPX_MARK(5)
-        if constexpr (TMEM_IO) { if (p.sched & 1) stagger(p.skew_ns, tid); }
+        if ((TMEM_IO || (p.sched & 64)) && (p.sched & 1)) stagger(p.skew_ns, tid);
 
         // ---- inverse stage 0: smem -> twiddle -> butterfly -> global
         {

@@ -218,7 +218,7 @@ def test_tma_and_direct_load_paths_agree(fb, oracle, dev):
             lib.spectre_mix_set_tma(1)
             lib.spectre_mix_set_tmem(1)
             lib.spectre_mix_set_prefetch(0)
-            lib.spectre_mix_set_skew_ns(-300)
+            lib.spectre_mix_set_skew_ns(-350)
             lib.spectre_mix_set_sched(3)
         y5 = fb.spectral_mix(*args, n_fft=n_fft, group_width=dg)   # defaults again
         assert torch.equal(y0, y1) and torch.equal(y1, y2) and torch.equal(y1, y3) and torch.equal(y1, y4) and torch.equal(y1, y5)

@@ -24,13 +24,13 @@ def check(skew, sched, pf):
     for _ in range(2):
         ok &= bool(torch.equal(fft_b200.spectral_mix(V, g, None, n_fft=4096, group_width=16), ref))
     return ok
-for skew, sched in [(0, 8), (-300, 11), (-300, 3), (0, 0), (-300, 7), (-300, 3), (-450, 3), (-150, 3)]:
+for skew, sched in [(-300, 3), (-200, 3), (-250, 3), (-300, 3), (-350, 3), (-400, 3), (-100300, 3), (-100500, 3), (-200300, 3), (-200500, 3), (-300, 3), (-300, 2), (-250, 2)]:
     for pf in (0,):
         ok = check(skew, sched, pf) if not (sched & 12) else None
         lib.spectre_mix_set_skew_ns(skew); lib.spectre_mix_set_sched(sched)
         r = time_case(lib, 4096, 768, 16, 128, 0, pf, tma=1, tmem=1, reps=40)
         tiles = 128 * 96 / 148.0
         print(json.dumps(dict(skew=skew, sched=sched, prefetch=pf, exact=ok, GBps=round(r["GBps"]), ms=round(r["ms"], 4), us_per_tile=round(r["ms"] * 1e3 / tiles, 2))), flush=True)
-lib.spectre_mix_set_skew_ns(-300); lib.spectre_mix_set_sched(3); lib.spectre_mix_set_prefetch(0)
+lib.spectre_mix_set_skew_ns(-350); lib.spectre_mix_set_sched(3); lib.spectre_mix_set_prefetch(0)
 PY
 done
