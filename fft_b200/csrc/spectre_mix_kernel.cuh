@@ -758,7 +758,7 @@ __global__ void __launch_bounds__(NT + ((TMA_IN && NT >= kSepProducerMinThreads)
     // TMEM_IO: the helper warpgroup parks the NEXT tile in tensor memory while this one is transformed and drains the
     // PREVIOUS tile's results from tensor memory, so loads, stores and the FFT passes of three tiles overlap although
     // shared memory holds only one.  Needs one stage-0 butterfly per thread and row blocks that are multiples of 128.
-    static_assert(!TMEM_IO || (SEP && sizeof(TIN) == 4 && sizeof(TOUT) == 4 && NT == NCOL * PL::L(0) && PL::L(0) % 128 == 0 &&
+    static_assert(!TMEM_IO || (SEP && sizeof(TIN) == sizeof(TOUT) && NT == NCOL * PL::L(0) && PL::L(0) % 128 == 0 &&
                                MINB == 1 && (PL::N * NCOL * 4) % 128 == 0 && PL::N * NCOL * 4 / 128 * 2 <= 512),
                   "TMEM staging: unsupported shape");
     constexpr int G128 = PL::L(0) / 128;                 // 128-row groups per stage-0 row block (column-group stride per m = G128 * NCOL)
@@ -953,8 +953,9 @@ __global__ void __launch_bounds__(NT + ((TMA_IN && NT >= kSepProducerMinThreads)
 #endif
 #pragma unroll 1
                 for (int k = 0; k < NBOX; ++k) {
-                    float4 *slot = reinterpret_cast<float4 *>(stg + sl * SLOTB);
-                    float4 v[GPB];
+                    // ring entries hold the tensor's own element type (4 fp32 or 4 bf16 channels); tensor memory always fp32
+                    LT *slot = reinterpret_cast<LT *>(stg + sl * SLOTB);
+                    Cx<float2> v[GPB];
 #if SPX_COOP_PF
                     if (pf) {
                         prefetch_l2(pf);
@@ -971,17 +972,17 @@ __global__ void __launch_bounds__(NT + ((TMA_IN && NT >= kSepProducerMinThreads)
                         c1 = clock64();
 #endif
 #pragma unroll
-                        for (int g = 0; g < GPB; ++g) v[g] = slot[g * 128 + hl];      // consecutive lanes, consecutive slots
+                        for (int g = 0; g < GPB; ++g) v[g] = Lin<MODE, TIN>::get(slot[g * 128 + hl]);   // consecutive lanes, consecutive entries
 #pragma unroll
-                        for (int g = 0; g < GPB; ++g) tmem_st4(tq + (uint32_t)(4 * (k * GPB + g)), v[g].x, v[g].y, v[g].z, v[g].w);
+                        for (int g = 0; g < GPB; ++g) tmem_st4(tq + (uint32_t)(4 * (k * GPB + g)), v[g].re.x, v[g].re.y, v[g].im.x, v[g].im.y);
                     }
                     if (do_drain) {
 #pragma unroll
-                        for (int g = 0; g < GPB; ++g) tmem_ld4(tq + (uint32_t)(TCOLS + 4 * (k * GPB + g)), v[g].x, v[g].y, v[g].z, v[g].w);
+                        for (int g = 0; g < GPB; ++g) tmem_ld4(tq + (uint32_t)(TCOLS + 4 * (k * GPB + g)), v[g].re.x, v[g].re.y, v[g].im.x, v[g].im.y);
                         tmem_wait_ld();
                         // every thread refills exactly the ring entries it has just read: no barrier in between
 #pragma unroll
-                        for (int g = 0; g < GPB; ++g) slot[g * 128 + hl] = v[g];
+                        for (int g = 0; g < GPB; ++g) slot[g * 128 + hl] = Lin<MODE, TOUT>::put(v[g]);
                         fence_proxy_async();
                     }
 #if SPX_HELPER_TL

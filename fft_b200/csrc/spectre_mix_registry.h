@@ -38,8 +38,8 @@ struct Launcher {
     }
     // TMA delivers rows of NCOL elements; the box's inner extent must be a multiple of 16 bytes
     static constexpr bool kTma = (MODE == MODE_QUAD) && ((sizeof(TIO) * 4 * NCOL) % 16 == 0);
-    // TMEM staging: fp32 packed tiles, one stage-0 butterfly per thread, 1 CTA per SM, two tiles fit the 512 columns
-    static constexpr bool kTmem = kTma && sizeof(TIO) == 4 && NT >= kSepProducerMinThreads && NT == NCOL * PL::L(0) &&
+    // TMEM staging: packed tiles (fp32 or bf16 in HBM, fp32 in tensor memory), one stage-0 butterfly per thread, 1 CTA per SM, two tiles fit the 512 columns
+    static constexpr bool kTmem = kTma && NT >= kSepProducerMinThreads && NT == NCOL * PL::L(0) &&
                                   PL::L(0) % 128 == 0 && MINB == 1 && (PL::N * NCOL * 4 / 128 * 2 <= 512);
     template <bool HAS_MEM, bool TMA, bool TMEM>
     static const void *fn() {

@@ -86,6 +86,7 @@ SWEEP = [
     # channel counts that leave a partial tile, group widths for every element mode
     (2, 1024, 1024, 24, 8, True),        # QUAD, C not a multiple of the tile
     (2, 4096, 4096, 40, 8, False),
+    (3, 4096, 4096, 96, 12, True),       # QUAD with a group width that is not a power of two (division path of the tile loop)
     (2, 256, 256, 36, 6, True),          # PAIR (d_g even, not /4)
     (2, 1024, 1024, 20, 10, False),
     (2, 256, 256, 15, 3, True),          # REAL (odd group width)
