@@ -154,7 +154,7 @@ int spectre_mix_set_l2_promotion(int level);
  * around the last inverse pass's shared-memory read. */
 int spectre_mix_set_sched(int flags);
 
-/* Debug: device buffer of grid * 4 thread groups * 8 tiles * 8 uint64 that receives per-phase %globaltimer stamps
+/* Debug: device buffer of grid * 5 groups (4 compute thread groups + the helper warpgroup) * 8 tiles * 8 uint64 that receives per-phase %globaltimer stamps
  * (NULL = off). */
 int spectre_mix_set_timeline(void *device_buffer);
 
