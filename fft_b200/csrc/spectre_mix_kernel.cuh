@@ -567,7 +567,8 @@ __device__ __forceinline__ void helper_bar() { asm volatile("bar.sync 2, 128;" :
 // Warp stagger: the four warps that share a scheduler (warp id / 4 = "slot" 0..3) leave a CTA barrier in lock step and would
 // all load, then all compute, then all store.  Holding slot s back by s * clk cycles lets the shared-memory phase of one warp
 // run under the butterflies of another.  code > 0: legacy nanosleep of slots 1 and 3; code < 0: clock spin, |code| % 100000
-// cycles per step, |code| / 100000 selects the grouping (0: four steps, 1: slots {0,1} vs {2,3}, 2: even vs odd slots).
+// cycles per step, |code| / 100000 selects the grouping (0: four steps, 1: slots {0,1} vs {2,3}, 2: even vs odd slots,
+// 3: four steps plus a quarter step per scheduler, 4: four steps by __nanosleep instead of a clock spin).
 __device__ __forceinline__ void stagger(int code, int tid) {
     if (code == 0) return;
     if (code > 0) {
@@ -578,7 +579,12 @@ __device__ __forceinline__ void stagger(int code, int tid) {
     int slot = (tid >> 7) & 3;
     if (grp == 1) slot >>= 1;
     else if (grp == 2) slot &= 1;
-    const int target = slot * clk;
+    int target = slot * clk;
+    if (grp == 3) target += ((tid >> 5) & 3) * (clk >> 2);   // 16 distinct offsets: the schedulers' warps a quarter step apart
+    if (grp == 4) {                                            // sleep instead of spinning (no issue slots while waiting)
+        if (target > 0) __nanosleep((unsigned)(target / 2));   // ~2 clocks per ns
+        return;
+    }
     const int t0 = (int)clock();
     while ((int)clock() - t0 < target) {}
 }

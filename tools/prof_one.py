@@ -18,12 +18,15 @@ ap.add_argument("--group-width", type=int, default=16)
 ap.add_argument("--tile", type=int, default=0)
 ap.add_argument("--prefetch", type=int, default=0)
 ap.add_argument("--reps", type=int, default=4)
+ap.add_argument("--sched", type=int, default=None, help="scheduling / diagnostic flags (4: tile I/O only, 8: FFT passes only)")
 ap.add_argument("--bf16", action="store_true")
 ap.add_argument("--mem", action="store_true")
 a = ap.parse_args()
 lib = _lib.load()
 lib.spectre_mix_set_tile_channels(a.tile)
 lib.spectre_mix_set_prefetch(a.prefetch)
+if a.sched is not None:
+    lib.spectre_mix_set_sched(a.sched)
 dev = torch.device("cuda")
 V = torch.randn(a.batch, a.n_fft, a.channels, device=dev)
 if a.bf16:
