@@ -505,3 +505,26 @@ def test_randomised_shapes(fb, oracle, dev):
         got = fb.spectral_mix(Vd, gate.to(dev), None if mem is None else mem.to(dev), n_fft=n_fft, group_width=dg)
         e1, e2 = rel_l2(got.cpu().numpy(), want), max_abs_rel(got.cpu().numpy(), want)
         assert e1 <= REL_L2_F32 and e2 <= MAX_ABS_F32, (trial, B, N, n_fft, C, dg, with_mem, e1, e2)
+
+
+def test_cuda_graph_capture_and_second_stream(fb, dev):
+    """The op is asynchronous on the current stream and holds no per-call host state: it can be captured into a CUDA graph
+    after a warm-up call (twiddle tables / tensor maps are built on first use) and replayed, and it runs on a side stream."""
+    V, gate, _ = _rand_case(3, 4096, 4096, 64, 16, False, seed=77)
+    Vd, gd = V.to(dev), gate.to(dev)
+    want = fb.spectral_mix(Vd, gd, n_fft=4096, group_width=16).clone()          # warm-up, eager result
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        y_side = fb.spectral_mix(Vd, gd, n_fft=4096, group_width=16)
+    torch.cuda.current_stream().wait_stream(side)
+    assert torch.equal(y_side, want)
+    static_in = Vd.clone()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        static_out = fb.spectral_mix(static_in, gd, n_fft=4096, group_width=16)
+    static_in.copy_(2.0 * Vd)                                                   # new data, same buffers
+    graph.replay()
+    torch.cuda.synchronize()
+    ref2 = fb.spectral_mix(2.0 * Vd, gd, n_fft=4096, group_width=16)
+    assert torch.equal(static_out, ref2)
