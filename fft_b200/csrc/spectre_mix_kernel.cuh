@@ -257,6 +257,23 @@ __device__ __forceinline__ float2 tw_get(const float2 *tw_s, const float2 *tw_g,
     else return __ldg(tw_g + PL::TWOFF(S_) + idx);
 }
 
+// radix-16 twiddles from the six stored rows: a[q1] = W^{u q1}, b[q0] = W^{4 u q0} (index 0 unused)
+template <class V>
+__device__ __forceinline__ void apply_twiddles16(Cx<V> (&x)[16], const float2 (&a)[4], const float2 (&b)[4]) {
+#pragma unroll
+    for (int q0 = 0; q0 < 4; ++q0)
+#pragma unroll
+        for (int q1 = 0; q1 < 4; ++q1) {
+            const int q = q1 + 4 * q0;
+            if (q == 0) continue;
+            float2 w;
+            if (q0 == 0) w = a[q1];
+            else if (q1 == 0) w = b[q0];
+            else w = make_float2(fmaf(-a[q1].y, b[q0].y, a[q1].x * b[q0].x), fmaf(a[q1].x, b[q0].y, a[q1].y * b[q0].x));
+            x[q] = cmul(x[q], w.x, w.y);
+        }
+}
+
 // x[q] *= W^{u q}, q = 1 .. R-1, for stage S_ (forward sign; the inverse passes call it on (im, re)-swapped data)
 template <class PL, int S_, class V>
 __device__ __forceinline__ void apply_twiddles(Cx<V> (&x)[PL::R(S_)], const float2 *tw_s, const float2 *tw_g, int u) {
@@ -268,18 +285,7 @@ __device__ __forceinline__ void apply_twiddles(Cx<V> (&x)[PL::R(S_)], const floa
             a[j] = tw_get<PL, S_>(tw_s, tw_g, (j - 1) * L + u);
             b[j] = tw_get<PL, S_>(tw_s, tw_g, (j + 2) * L + u);
         }
-#pragma unroll
-        for (int q0 = 0; q0 < 4; ++q0)
-#pragma unroll
-            for (int q1 = 0; q1 < 4; ++q1) {
-                const int q = q1 + 4 * q0;
-                if (q == 0) continue;
-                float2 w;
-                if (q0 == 0) w = a[q1];
-                else if (q1 == 0) w = b[q0];
-                else w = make_float2(fmaf(-a[q1].y, b[q0].y, a[q1].x * b[q0].x), fmaf(a[q1].x, b[q0].y, a[q1].y * b[q0].x));
-                x[q] = cmul(x[q], w.x, w.y);
-            }
+        apply_twiddles16(x, a, b);
     } else {
 #pragma unroll
         for (int q = 1; q < R; ++q) {
@@ -288,7 +294,6 @@ __device__ __forceinline__ void apply_twiddles(Cx<V> (&x)[PL::R(S_)], const floa
         }
     }
 }
-
 // ------------------------------------------------------------------ element traits per mode
 template <int MODE>
 struct Elem;
