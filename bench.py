@@ -135,6 +135,25 @@ def cpu_reference_path(torch, batch: int, min_seconds: float, max_reps: int):
     return {"tokens": batch * SEQ, "times": times, "threads": torch.get_num_threads()}
 
 
+def gpu_local_cpus(torch, index: int):
+    """CPUs of the NUMA node the GPU hangs off (sysfs), or None: pinned host buffers allocated from there keep the
+    host-buffer leg's PCIe copies off the inter-socket link."""
+    try:
+        pr = torch.cuda.get_device_properties(index)
+        bdf = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        return (node, cpus) if cpus else None
+    except Exception:  # noqa: BLE001 -- no sysfs / no NUMA information: leave the affinity alone
+        return None
+
+
 def run_reference(args):
     """--impl reference: the CPU implementation of the path, all host threads, bounded sample per step."""
     rank = int(os.environ.get("RANK", "0"))
@@ -260,6 +279,11 @@ def main():
 
     # ---- e2e: host buffers through the C-ABI host entry (H2D + kernel + D2H inside the timed region)
     Be = args.e2e_batch
+    # allocate (first-touch) and drive the host buffers from the GPU's own NUMA node when sysfs tells which one that is
+    saved_affinity = os.sched_getaffinity(0)
+    near = gpu_local_cpus(torch, local_rank)
+    if near is not None:
+        os.sched_setaffinity(0, near[1])
     hV = torch.randn(Be, SEQ, D_MODEL, generator=torch.Generator().manual_seed(100 + rank)).pin_memory()
     hg = torch.randn(Be, NG, F_HALF, dtype=torch.cfloat, generator=torch.Generator().manual_seed(200 + rank)).pin_memory()
     ho = torch.empty(Be, SEQ, D_MODEL).pin_memory()
@@ -276,9 +300,11 @@ def main():
     if dist is not None:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = Be * SEQ * world * args.e2e_steps / float(te.item())
+    os.sched_setaffinity(0, saved_affinity)
     e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(hV.numel() * 4 + hg.numel() * 8),
            "d2h_bytes_per_step": int(ho.numel() * 4), "batch_per_gpu": Be, "steps": args.e2e_steps,
-           "entry": "spectre_mix_fwd_host (C ABI, pinned host buffers, chunked H2D/kernel/D2H on 4 streams)"}
+           "entry": "spectre_mix_fwd_host (C ABI, pinned host buffers, chunked H2D/kernel/D2H on 4 streams)",
+           "host_numa_node": None if near is None else near[0]}
 
     # ---- CPU baseline beside it (rank 0 at N=1 only)
     cpu = None

@@ -11,6 +11,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <map>
 #include <mutex>
 #include <string>
@@ -593,9 +594,15 @@ int spectre_mix_fwd_host(const float *v, const float *gate, const float *mem, fl
     HostCtx &h = g_host[dev];
     const size_t fh = n_fft / 2 + 1, ng = C / group_width;
     const size_t row_v = (size_t)N * C * 4, row_o = (size_t)n_io * C * 4, row_g = ng * fh * 8;
-    // batch rows per chunk: ~16 MB of V per chunk -- the call is PCIe-bound, so short chunks (a short pipeline fill before
-    // both copy engines run and a short drain after) matter more than filling every SM with one launch
-    const int rows = (int)std::max<size_t>(1, std::min<size_t>((size_t)B, (16u << 20) / std::max<size_t>(row_v, 1)));
+    // batch rows per chunk: ~32 MB of V per chunk -- the call is PCIe-bound, so short chunks (a short pipeline fill before
+    // both copy engines run and a short drain after) matter more than filling every SM with one launch; measured on the
+    // metric shape: 13 MB 1.25e7, 26-52 MB 1.34e7, 104 MB 1.26e7, 208 MB 1.10e7 tokens/s
+    size_t chunk_bytes = 32u << 20;
+    if (const char *env = getenv("SPECTRE_MIX_HOST_CHUNK_MB")) {   // experiment knob
+        const long mb = strtol(env, nullptr, 10);
+        if (mb > 0 && mb <= 4096) chunk_bytes = (size_t)mb << 20;
+    }
+    const int rows = (int)std::max<size_t>(1, std::min<size_t>((size_t)B, chunk_bytes / std::max<size_t>(row_v, 1)));
     const size_t need_v = std::max(row_v, row_o) * rows, need_g = row_g * rows;
     for (int i = 0; i < kHostStreams; ++i) {
         if (!h.s[i] && (e = cudaStreamCreateWithFlags(&h.s[i], cudaStreamNonBlocking)) != cudaSuccess)
