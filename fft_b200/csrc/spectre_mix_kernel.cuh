@@ -1353,7 +1353,11 @@ __global__ void __launch_bounds__(NT + ((TMA_IN && NT >= kSepProducerMinThreads)
             }
         }
         SPX_MARK(5)
-        if ((TMEM_IO || (p.sched & 64)) && (p.sched & 1)) stagger(p.skew_ns, tid);
+        if ((TMEM_IO || (p.sched & 64)) && (p.sched & 1)) {
+            // sched bits 8..11: step of this second stagger in quarters of the first one's (0 = same step)
+            const int q4 = (p.sched >> 8) & 15;
+            stagger((q4 && p.skew_ns < 0) ? -(((-p.skew_ns) / 100000) * 100000 + (((-p.skew_ns) % 100000) * q4) / 4) : p.skew_ns, tid);
+        }
 
         // ---- inverse stage 0: smem -> twiddle -> butterfly -> global
         {
