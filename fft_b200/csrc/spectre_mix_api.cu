@@ -49,6 +49,7 @@ int g_use_tmem = 1;
 int g_skew_ns = -350;   // warp stagger after the CTA barriers (see stagger() in the kernel header)
 int g_sched = 3;          // bit 0 stagger before the last inverse pass too, bit 1 split barrier around its read
 int g_use_two_pass = 1;
+int g_long_chunk_mb = 0;  // long-context path: rows per chunk sized so the intermediate stays in L2 (0 = whole batch at once)
 int g_l2_promo = 0;       // L2 promotion of the input tensor map: 0 none, 1 64 B, 2 128 B, 3 256 B
 unsigned long long *g_timeline = nullptr;
 
@@ -293,20 +294,10 @@ const KernelEntry *find_sub_kernel() {
 
 // pre pass (radix-R stage + twiddles) -> 4096-point shared-memory kernel on R interleaved sub-transforms (in place in
 // the scratch tensor) -> post pass.  Three launches, each streaming the tensor once.
-int mix_two_pass(DeviceState &st, const KernelEntry &k, const void *v, int dtype, long long v_sb, long long v_sn, const void *gate,
-                 const void *mem, long long mem_stride, void *out, long long o_sb, long long o_sn, int B, int n_io, int n_fft,
-                 int C, int group_width, cudaStream_t stream) {
+int mix_two_pass_rows(DeviceState &st, const KernelEntry &k, const void *v, int dtype, long long v_sb, long long v_sn, const void *gate,
+                      const void *mem, long long mem_stride, void *out, long long o_sb, long long o_sn, int B, int n_io, int n_fft,
+                      int C, int group_width, float *scr, cudaStream_t stream) {
     const int sub = 4096, R = n_fft / sub;
-    const size_t need = (size_t)B * n_fft * C * sizeof(float);
-    if (need > st.scratch_bytes) {
-        if (st.scratch) cudaFree(st.scratch);
-        st.scratch = nullptr;
-        st.scratch_bytes = 0;
-        cudaError_t e = cudaMalloc(&st.scratch, need);
-        if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(long-context scratch)");
-        st.scratch_bytes = need;
-    }
-    float *scr = reinterpret_cast<float *>(st.scratch);
     cudaError_t e = spx::long_pass(true, R, dtype == SPECTRE_MIX_BF16, v, scr, v_sb, v_sn, B, n_io, C, sub, st.sm_count, stream);
     if (e != cudaSuccess) return cuda_fail(e, "long-context pre pass");
 
@@ -356,6 +347,39 @@ int mix_two_pass(DeviceState &st, const KernelEntry &k, const void *v, int dtype
 
     e = spx::long_pass(false, R, dtype == SPECTRE_MIX_BF16, scr, out, o_sb, o_sn, B, n_io, C, sub, st.sm_count, stream);
     if (e != cudaSuccess) return cuda_fail(e, "long-context post pass");
+    return 0;
+}
+
+// The batch is walked in chunks of rows whose complex intermediate (n_fft x C x 4 B per row) is small enough to stay in the
+// 126 MB L2 between the three launches: the intermediate is then written, transformed in place and read back without ever
+// reaching HBM (the same scratch lines are overwritten by the next chunk), so HBM sees V once and the output once.
+int mix_two_pass(DeviceState &st, const KernelEntry &k, const void *v, int dtype, long long v_sb, long long v_sn, const void *gate,
+                 const void *mem, long long mem_stride, void *out, long long o_sb, long long o_sn, int B, int n_io, int n_fft,
+                 int C, int group_width, cudaStream_t stream) {
+    const size_t row_bytes = (size_t)n_fft * C * sizeof(float);
+    size_t chunk_mb = g_long_chunk_mb;
+    if (const char *env = getenv("SPECTRE_MIX_LONG_CHUNK_MB")) chunk_mb = (size_t)std::max(0L, strtol(env, nullptr, 10));   // experiment knob
+    int rows = chunk_mb == 0 ? B : (int)std::max<size_t>(1, std::min<size_t>((size_t)B, (chunk_mb << 20) / std::max<size_t>(row_bytes, 1)));
+    const size_t need = (size_t)rows * row_bytes;
+    if (need > st.scratch_bytes) {
+        if (st.scratch) cudaFree(st.scratch);
+        st.scratch = nullptr;
+        st.scratch_bytes = 0;
+        cudaError_t e = cudaMalloc(&st.scratch, need);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(long-context scratch)");
+        st.scratch_bytes = need;
+    }
+    float *scr = reinterpret_cast<float *>(st.scratch);
+    const size_t es = dtype == SPECTRE_MIX_F32 ? 4 : 2;
+    const size_t gate_row = (size_t)(C / group_width) * (n_fft / 2 + 1) * sizeof(float2);
+    for (int b0 = 0; b0 < B; b0 += rows) {
+        const int nb = std::min(rows, B - b0);
+        int rc = mix_two_pass_rows(st, k, reinterpret_cast<const char *>(v) + (size_t)b0 * v_sb * es, dtype, v_sb, v_sn,
+                                   reinterpret_cast<const char *>(gate) + (size_t)b0 * gate_row, mem, mem_stride,
+                                   reinterpret_cast<char *>(out) + (size_t)b0 * o_sb * es, o_sb, o_sn, nb, n_io, n_fft, C, group_width,
+                                   scr, stream);
+        if (rc) return rc;
+    }
     return 0;
 }
 
