@@ -25,10 +25,12 @@
 //     twiddle table serves both directions.
 //   * Shared-memory element index e is stored at e + (e >> 4): every pass (strides
 //     n_fft/r, 16, 1) is bank-conflict free with 128-bit accesses.
-//   * Loads/stores are 128-bit, sector-complete per warp instruction; the next
-//     tile of a CTA is prefetched into the 126 MB L2 while the current one is
-//     being transformed (L2 is the landing buffer -- a 4096x8 fp32 tile fills
-//     shared memory on its own).
+//   * Tile I/O goes through TMA (cp.async.bulk.tensor) wherever the layout allows; at n_fft = 4096 a helper
+//     warpgroup parks the NEXT tile in tensor memory and drains the PREVIOUS tile's results from it through one
+//     ring of TMA boxes while the 16 compute warps run the FFT passes (TMEM_IO variant, fp32 and bf16 rows).
+//   * A radix-16 stage keeps 6 of its 15 twiddle rows in shared memory and forms the rest as scalar products.
+//   * Compute warps are staggered per scheduler slot after the CTA barriers and the barrier around the last
+//     pass's read is split (arrive / wait), so shared-memory phases of one warp run under another's butterflies.
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>
