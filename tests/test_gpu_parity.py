@@ -528,3 +528,14 @@ def test_cuda_graph_capture_and_second_stream(fb, dev):
     torch.cuda.synchronize()
     ref2 = fb.spectral_mix(2.0 * Vd, gd, n_fft=4096, group_width=16)
     assert torch.equal(static_out, ref2)
+
+
+def test_tmem_variants_race_hunt():
+    """Random batch / channel / row counts and dtypes at n_fft = 4096: the TMEM-staged variants under the default schedule
+    (helper warpgroup phases, warp stagger, split barrier) agree bit for bit with the plain TMA variant."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "stress_4096.py"), "40", "7"], capture_output=True, text=True,
+                       timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
