@@ -533,6 +533,7 @@ def test_cuda_graph_capture_and_second_stream(fb, dev):
 def test_tmem_variants_race_hunt():
     """Random batch / channel / row counts and dtypes at n_fft = 4096: the TMEM-staged variants under the default schedule
     (helper warpgroup phases, warp stagger, split barrier) agree bit for bit with the plain TMA variant."""
+    import os
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
