@@ -227,6 +227,9 @@ constexpr int kTmemSlotsMax = 7;
 template <class PL>
 __host__ __device__ constexpr int tmem_slots() { return PL::kSub ? 6 : kTmemSlotsMax; }
 // register split of the TMEM variant (512 compute + 128 helper threads, 96 per thread at launch = 61440 in the CTA pool)
+#ifndef SPX_ILV
+#define SPX_ILV 1
+#endif
 #ifndef SPX_SPLIT_DUTY
 #define SPX_SPLIT_DUTY 1
 #endif
@@ -433,7 +436,7 @@ __device__ __forceinline__ int klow_of(int Q) {
 // ------------------------------------------------------------------ in-place inner passes (stages 1 .. NS-2)
 // Butterfly bf = Q * L + u of a column works on elements Q*(R*L) + m*L + u, m < R, and leaves output
 // digit q in the slot of input m = q, so no pass ever moves data between slots.
-template <class PL, int MODE, int NCOL, int NT, int S_>
+template <class PL, int MODE, int NCOL, int NT, int S_, bool ILV = false>
 __device__ __forceinline__ void fwd_inner_pass(typename Elem<MODE>::S *buf, const float2 *tw, const float2 *twg, int tid) {
     using E = Elem<MODE>;
     using V = typename E::V;
@@ -441,7 +444,8 @@ __device__ __forceinline__ void fwd_inner_pass(typename Elem<MODE>::S *buf, cons
     constexpr int CS = Smem<PL, MODE, NCOL>::CS;
     static_assert(L % 16 == 0 || L == 1, "offset padding assumes 16 | L");
     for (int w = tid; w < ITEMS; w += NT) {
-        const int col = w / NBF, bf = w - col * NBF;
+        // ILV: the element columns are interleaved over adjacent lanes (both columns of a butterfly id share twiddles / gate)
+        const int col = ILV ? w % NCOL : w / NBF, bf = ILV ? w / NCOL : w - col * NBF;
         const int Q = bf / L, u = bf - Q * L;
         const int e0 = Q * (R * L) + u;
         typename E::S *cb = buf + col * CS + e0 + (e0 >> 4);
@@ -456,14 +460,15 @@ __device__ __forceinline__ void fwd_inner_pass(typename Elem<MODE>::S *buf, cons
 }
 
 // inverse of the above: conj-twiddle then inverse butterfly, done as forward arithmetic on (im, re)
-template <class PL, int MODE, int NCOL, int NT, int S_>
+template <class PL, int MODE, int NCOL, int NT, int S_, bool ILV = false>
 __device__ __forceinline__ void inv_inner_pass(typename Elem<MODE>::S *buf, const float2 *tw, const float2 *twg, int tid) {
     using E = Elem<MODE>;
     using V = typename E::V;
     constexpr int R = PL::R(S_), L = PL::L(S_), NBF = PL::N / R, ITEMS = NCOL * NBF;
     constexpr int CS = Smem<PL, MODE, NCOL>::CS;
     for (int w = tid; w < ITEMS; w += NT) {
-        const int col = w / NBF, bf = w - col * NBF;
+        // ILV: the element columns are interleaved over adjacent lanes (both columns of a butterfly id share twiddles / gate)
+        const int col = ILV ? w % NCOL : w / NBF, bf = ILV ? w / NCOL : w - col * NBF;
         const int Q = bf / L, u = bf - Q * L;
         const int e0 = Q * (R * L) + u;
         typename E::S *cb = buf + col * CS + e0 + (e0 >> 4);
@@ -751,6 +756,9 @@ __global__ void __launch_bounds__(NT + ((TMA_IN && NT >= kSepProducerMinThreads)
     constexpr bool kWarpLocal = (NS >= 3) && (PL::R(NS - 1) == 16) && (PL::R(NS - 2) == 16) && (NT % 32 == 0) &&
                                 ((NCOL * (N / 16)) % NT == 0 || NT % (NCOL * (N / 16)) == 0) && ((N / 16) % 32 == 0);
 
+    // inner passes and the middle pass map (column, butterfly) -> thread with the two element columns on adjacent lanes: gate and
+    // twiddle reads of a lane pair coincide (one wavefront instead of two); the exchanges stay inside a warp
+    constexpr bool kIlv = (SPX_ILV != 0) && TMEM_IO && kWarpLocal && NS == 3 && NCOL == 2 && MODE == MODE_QUAD;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     S *buf = reinterpret_cast<S *>(smem_raw);
     float2 *tw = reinterpret_cast<float2 *>(smem_raw + SM::data_bytes);
@@ -1241,15 +1249,15 @@ __global__ void __launch_bounds__(NT + ((TMA_IN && NT >= kSepProducerMinThreads)
         // The exchange between stage NS-2 and the middle pass is a 16x16 transpose among the 16 threads that share
         // (column, leading digits): with consecutive butterflies on consecutive lanes those threads are one half-warp,
         // in this pass and in the middle pass alike, so __syncwarp() orders it and warps run on unsynchronised.
-        if constexpr (NS > 2) { fwd_inner_pass<PL, MODE, NCOL, NT, 1>(buf, tw, p.tw, tid); if constexpr (NS == 3 && kWarpLocal) __syncwarp(); else cta_sync<NT, SEP>(); }
-        if constexpr (NS > 3) { fwd_inner_pass<PL, MODE, NCOL, NT, 2>(buf, tw, p.tw, tid); if constexpr (kWarpLocal) __syncwarp(); else cta_sync<NT, SEP>(); }
+        if constexpr (NS > 2) { fwd_inner_pass<PL, MODE, NCOL, NT, 1, kIlv>(buf, tw, p.tw, tid); if constexpr (NS == 3 && kWarpLocal) __syncwarp(); else cta_sync<NT, SEP>(); }
+        if constexpr (NS > 3) { fwd_inner_pass<PL, MODE, NCOL, NT, 2, kIlv>(buf, tw, p.tw, tid); if constexpr (kWarpLocal) __syncwarp(); else cta_sync<NT, SEP>(); }
 
         SPX_MARK(3)
         // ---- middle pass: last forward butterfly -> gate (+memory) -> first inverse butterfly
         {
             constexpr int NBF = N / RL, ITEMS = NCOL * NBF;
             for (int w = tid; w < ITEMS; w += NT) {
-                const int col = w / NBF, Q = w - col * NBF;
+                const int col = kIlv ? w % NCOL : w / NBF, Q = kIlv ? w / NCOL : w - col * NBF;
                 if ((ce0 + col) >= CE) continue;   // column past the last channel: nothing to transform
                 const int e0 = Q * RL;
                 S *cb = buf + col * CS + e0 + (e0 >> 4);
@@ -1338,8 +1346,8 @@ __global__ void __launch_bounds__(NT + ((TMA_IN && NT >= kSepProducerMinThreads)
         }
 
         // ---- inverse stages NS-2 .. 1: smem -> twiddle -> butterfly -> smem (in place)
-        if constexpr (NS > 3) { inv_inner_pass<PL, MODE, NCOL, NT, 2>(buf, tw, p.tw, tid); cta_sync<NT, SEP>(); }
-        if constexpr (NS > 2) { inv_inner_pass<PL, MODE, NCOL, NT, 1>(buf, tw, p.tw, tid); cta_sync<NT, SEP>(); }
+        if constexpr (NS > 3) { inv_inner_pass<PL, MODE, NCOL, NT, 2, kIlv>(buf, tw, p.tw, tid); cta_sync<NT, SEP>(); }
+        if constexpr (NS > 2) { inv_inner_pass<PL, MODE, NCOL, NT, 1, kIlv>(buf, tw, p.tw, tid); cta_sync<NT, SEP>(); }
         if (fetch_next) {
             if constexpr (SUB) {
                 gate_put_sub<N, NT, GKS>(gate_s, gnext, tid, nq, p.sub_R, p.inv_n);
