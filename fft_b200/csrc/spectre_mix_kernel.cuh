@@ -227,9 +227,6 @@ constexpr int kTmemSlotsMax = 7;
 template <class PL>
 __host__ __device__ constexpr int tmem_slots() { return PL::kSub ? 6 : kTmemSlotsMax; }
 // register split of the TMEM variant (512 compute + 128 helper threads, 96 per thread at launch = 61440 in the CTA pool)
-#ifndef SPX_TW1_REGS
-#define SPX_TW1_REGS 0
-#endif
 #ifndef SPX_ILV
 #define SPX_ILV 1
 #endif
@@ -440,8 +437,7 @@ __device__ __forceinline__ int klow_of(int Q) {
 // Butterfly bf = Q * L + u of a column works on elements Q*(R*L) + m*L + u, m < R, and leaves output
 // digit q in the slot of input m = q, so no pass ever moves data between slots.
 template <class PL, int MODE, int NCOL, int NT, int S_, bool ILV = false>
-__device__ __forceinline__ void fwd_inner_pass(typename Elem<MODE>::S *buf, const float2 *tw, const float2 *twg, int tid,
-                                               const float2 (*pa)[4] = nullptr, const float2 (*pb)[4] = nullptr) {
+__device__ __forceinline__ void fwd_inner_pass(typename Elem<MODE>::S *buf, const float2 *tw, const float2 *twg, int tid) {
     using E = Elem<MODE>;
     using V = typename E::V;
     constexpr int R = PL::R(S_), L = PL::L(S_), NBF = PL::N / R, ITEMS = NCOL * NBF;
@@ -457,8 +453,7 @@ __device__ __forceinline__ void fwd_inner_pass(typename Elem<MODE>::S *buf, cons
 #pragma unroll
         for (int m = 0; m < R; ++m) x[m] = E::unpack(cb[m * L + ((m * L) >> 4)]);
         Dft<R, V>::run(x);
-        if constexpr (R == 16) { if (pa) apply_twiddles16(x, *pa, *pb); else apply_twiddles<PL, S_, V>(x, tw, twg, u); }
-        else apply_twiddles<PL, S_, V>(x, tw, twg, u);
+        apply_twiddles<PL, S_, V>(x, tw, twg, u);
 #pragma unroll
         for (int q = 0; q < R; ++q) cb[q * L + ((q * L) >> 4)] = E::pack(x[q]);
     }
@@ -466,8 +461,7 @@ __device__ __forceinline__ void fwd_inner_pass(typename Elem<MODE>::S *buf, cons
 
 // inverse of the above: conj-twiddle then inverse butterfly, done as forward arithmetic on (im, re)
 template <class PL, int MODE, int NCOL, int NT, int S_, bool ILV = false>
-__device__ __forceinline__ void inv_inner_pass(typename Elem<MODE>::S *buf, const float2 *tw, const float2 *twg, int tid,
-                                               const float2 (*pa)[4] = nullptr, const float2 (*pb)[4] = nullptr) {
+__device__ __forceinline__ void inv_inner_pass(typename Elem<MODE>::S *buf, const float2 *tw, const float2 *twg, int tid) {
     using E = Elem<MODE>;
     using V = typename E::V;
     constexpr int R = PL::R(S_), L = PL::L(S_), NBF = PL::N / R, ITEMS = NCOL * NBF;
@@ -481,8 +475,7 @@ __device__ __forceinline__ void inv_inner_pass(typename Elem<MODE>::S *buf, cons
         Cx<V> x[R];
 #pragma unroll
         for (int q = 0; q < R; ++q) x[q] = cswap(E::unpack(cb[q * L + ((q * L) >> 4)]));
-        if constexpr (R == 16) { if (pa) apply_twiddles16(x, *pa, *pb); else apply_twiddles<PL, S_, V>(x, tw, twg, u); }
-        else apply_twiddles<PL, S_, V>(x, tw, twg, u);
+        apply_twiddles<PL, S_, V>(x, tw, twg, u);
         Dft<R, V>::run(x);
 #pragma unroll
         for (int m = 0; m < R; ++m) cb[m * L + ((m * L) >> 4)] = E::pack(cswap(x[m]));
@@ -1106,17 +1099,6 @@ __global__ void __launch_bounds__(NT + ((TMA_IN && NT >= kSepProducerMinThreads)
     int brow = (int)blockIdx.x / p.tiles_per_row, tcol = (int)blockIdx.x - brow * p.tiles_per_row;
     int nrow_ = 0, ncol_ = 0;
     auto gdiv = [&](int x) { return p.gw_shift >= 0 ? (x >> p.gw_shift) : x / p.group_width; };
-    // stage-1 twiddle rows of this thread's butterfly (its row offset u is the same for every tile): six values kept in registers
-    constexpr bool TW1R = (SPX_TW1_REGS != 0) && kIlv && PL::R(1) == 16 && (NCOL * (N / 16) == NT);
-    [[maybe_unused]] float2 tw1a[4], tw1b[4];
-    if constexpr (TW1R) {
-        const int u1 = (tid / NCOL) % PL::L(1);
-#pragma unroll
-        for (int j = 1; j < 4; ++j) {
-            tw1a[j] = tw_get<PL, 1>(tw, p.tw, (j - 1) * PL::L(1) + u1);
-            tw1b[j] = tw_get<PL, 1>(tw, p.tw, (j + 2) * PL::L(1) + u1);
-        }
-    }
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, brow = nrow_, tcol = ncol_) {
         nrow_ = brow + step_row;
         ncol_ = tcol + step_col;
@@ -1267,7 +1249,7 @@ __global__ void __launch_bounds__(NT + ((TMA_IN && NT >= kSepProducerMinThreads)
         // The exchange between stage NS-2 and the middle pass is a 16x16 transpose among the 16 threads that share
         // (column, leading digits): with consecutive butterflies on consecutive lanes those threads are one half-warp,
         // in this pass and in the middle pass alike, so __syncwarp() orders it and warps run on unsynchronised.
-        if constexpr (NS > 2) { fwd_inner_pass<PL, MODE, NCOL, NT, 1, kIlv>(buf, tw, p.tw, tid, TW1R ? &tw1a : nullptr, TW1R ? &tw1b : nullptr); if constexpr (NS == 3 && kWarpLocal) __syncwarp(); else cta_sync<NT, SEP>(); }
+        if constexpr (NS > 2) { fwd_inner_pass<PL, MODE, NCOL, NT, 1, kIlv>(buf, tw, p.tw, tid); if constexpr (NS == 3 && kWarpLocal) __syncwarp(); else cta_sync<NT, SEP>(); }
         if constexpr (NS > 3) { fwd_inner_pass<PL, MODE, NCOL, NT, 2, kIlv>(buf, tw, p.tw, tid); if constexpr (kWarpLocal) __syncwarp(); else cta_sync<NT, SEP>(); }
 
         SPX_MARK(3)
@@ -1365,7 +1347,7 @@ __global__ void __launch_bounds__(NT + ((TMA_IN && NT >= kSepProducerMinThreads)
 
         // ---- inverse stages NS-2 .. 1: smem -> twiddle -> butterfly -> smem (in place)
         if constexpr (NS > 3) { inv_inner_pass<PL, MODE, NCOL, NT, 2, kIlv>(buf, tw, p.tw, tid); cta_sync<NT, SEP>(); }
-        if constexpr (NS > 2) { inv_inner_pass<PL, MODE, NCOL, NT, 1, kIlv>(buf, tw, p.tw, tid, TW1R ? &tw1a : nullptr, TW1R ? &tw1b : nullptr); cta_sync<NT, SEP>(); }
+        if constexpr (NS > 2) { inv_inner_pass<PL, MODE, NCOL, NT, 1, kIlv>(buf, tw, p.tw, tid); cta_sync<NT, SEP>(); }
         if (fetch_next) {
             if constexpr (SUB) {
                 gate_put_sub<N, NT, GKS>(gate_s, gnext, tid, nq, p.sub_R, p.inv_n);
