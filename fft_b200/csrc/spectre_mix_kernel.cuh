@@ -222,10 +222,13 @@ struct Plan {
 __host__ __device__ constexpr int cmax(int a, int b) { return a > b ? a : b; }
 // ring of TMA boxes shared by both directions of the TMEM variant: while a tile is parked all but one slot hold
 // loads in flight (latency cover), while results are drained all of them are store sources
+#ifndef SPX_SUB_TW_SMEM
+#define SPX_SUB_TW_SMEM 1   // sub-transform variant: stage-0 twiddle rows in shared memory (12 KB) at the price of one ring slot
+#endif
 constexpr int kTmemSlotsMax = 7;
 // ring slots of a plan: the sub-transform variant holds a full-length gate table (two half-length slots) and has room for six
 template <class PL>
-__host__ __device__ constexpr int tmem_slots() { return PL::kSub ? 6 : kTmemSlotsMax; }
+__host__ __device__ constexpr int tmem_slots() { return PL::kSub ? (SPX_SUB_TW_SMEM ? 5 : 6) : kTmemSlotsMax; }
 // register split of the TMEM variant (512 compute + 128 helper threads, 96 per thread at launch = 61440 in the CTA pool)
 #ifndef SPX_ILV
 #define SPX_ILV 1
@@ -253,7 +256,7 @@ static_assert(kTmemHelperRegs % 8 == 0 && kTmemHelperRegs >= 24, "setmaxnreg tak
 // n_fft = 8192 the (largest) stage-0 table is read through L2 instead, at 16384 every table is.
 template <class PL>
 struct TwPolicy {
-    static constexpr int FROM = (PL::N >= 16384) ? (PL::NS - 1) : ((PL::N >= 8192 || PL::kSub) ? 1 : 0);
+    static constexpr int FROM = (PL::N >= 16384) ? (PL::NS - 1) : ((PL::N >= 8192 || (PL::kSub && !SPX_SUB_TW_SMEM)) ? 1 : 0);
     static constexpr int SMEM_N = PL::TWN - PL::TWOFF(FROM);   // entries held in shared memory
 };
 template <class PL, int S_>
