@@ -226,7 +226,8 @@ __host__ __device__ constexpr int cmax(int a, int b) { return a > b ? a : b; }
 #define SPX_SUB_TW_SMEM 1   // sub-transform variant: stage-0 twiddle rows in shared memory (12 KB) at the price of one ring slot
 #endif
 constexpr int kTmemSlotsMax = 7;
-// ring slots of a plan: the sub-transform variant holds a full-length gate table (two half-length slots) and has room for six
+// ring slots of a plan: the sub-transform variant holds a full-length gate table (two half-length slots) and has room for six,
+// or for five next to its stage-0 twiddle rows (measured faster: profiles/r01d_ab_sub_twiddles.txt)
 template <class PL>
 __host__ __device__ constexpr int tmem_slots() { return PL::kSub ? (SPX_SUB_TW_SMEM ? 5 : 6) : kTmemSlotsMax; }
 // register split of the TMEM variant (512 compute + 128 helper threads, 96 per thread at launch = 61440 in the CTA pool)
