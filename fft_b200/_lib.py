@@ -20,11 +20,15 @@ SYMBOLS = (
     "spectre_mix_abi_version",
     "spectre_mix_last_error",
     "spectre_mix_fwd",
+    "spectre_mix_fwd_ws",
+    "spectre_mix_workspace_bytes",
     "spectre_mix_fwd_host",
     "spectre_rfft_fwd",
     "spectre_decode_update",
     "spectre_decode_readout",
     "spectre_decode_step",
+    "spectre_decode_workspace_bytes",
+    "spectre_decode_gate",
     "spectre_gate_expand",
     "spectre_mix_plan",
     "spectre_mix_set_tile_channels",
@@ -50,6 +54,7 @@ class PlanInfo(ctypes.Structure):
         ("grid", ctypes.c_int),
         ("launches", ctypes.c_int),
         ("algorithmic_bytes", ctypes.c_int64),
+        ("workspace_bytes", ctypes.c_int64),
     ]
 
 
@@ -79,6 +84,11 @@ def load():
         lib.spectre_mix_last_error.argtypes = []
         lib.spectre_mix_fwd.restype = i32
         lib.spectre_mix_fwd.argtypes = [vp, i32, i64, i64, vp, vp, i64, vp, i32, i64, i64, i32, i32, i32, i32, i32, vp]
+        lib.spectre_mix_fwd_ws.restype = i32
+        lib.spectre_mix_fwd_ws.argtypes = [vp, i32, i64, i64, vp, vp, i64, vp, i32, i64, i64, i32, i32, i32, i32, i32, vp,
+                                           ctypes.c_size_t, vp]
+        lib.spectre_mix_workspace_bytes.restype = ctypes.c_size_t
+        lib.spectre_mix_workspace_bytes.argtypes = [i32, i32, i32, i32, i32, i32]
         lib.spectre_mix_fwd_host.restype = i32
         lib.spectre_mix_fwd_host.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32]
         lib.spectre_rfft_fwd.restype = i32
@@ -86,9 +96,13 @@ def load():
         lib.spectre_decode_update.restype = i32
         lib.spectre_decode_update.argtypes = [vp, vp, vp, i32, i32, ctypes.c_longlong, vp]
         lib.spectre_decode_readout.restype = i32
-        lib.spectre_decode_readout.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp]
+        lib.spectre_decode_readout.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp, ctypes.c_size_t, vp]
         lib.spectre_decode_step.restype = i32
-        lib.spectre_decode_step.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, ctypes.c_longlong, vp]
+        lib.spectre_decode_step.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, ctypes.c_longlong, vp, ctypes.c_size_t, vp]
+        lib.spectre_decode_workspace_bytes.restype = ctypes.c_size_t
+        lib.spectre_decode_workspace_bytes.argtypes = [i32, i32]
+        lib.spectre_decode_gate.restype = i32
+        lib.spectre_decode_gate.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, ctypes.c_longlong, i32, vp]
         lib.spectre_gate_expand.restype = i32
         lib.spectre_gate_expand.argtypes = [vp, vp, vp, vp, ctypes.c_longlong, vp, i32, i32, i32, i32, i32, vp]
         lib.spectre_mix_plan.restype = i32

@@ -16,6 +16,7 @@
 #include <stdint.h>
 
 #include "../../include/spectre_mix.h"
+#include "spectre_internal.h"
 
 namespace {
 
@@ -25,7 +26,7 @@ constexpr int kKChunk = 16;  // frequency bins per block
 template <int MODE>
 __global__ void __launch_bounds__(256) decode_kernel(float2 *__restrict__ prefix, const float *__restrict__ v_new,
                                                      const float *__restrict__ v_old, const float2 *__restrict__ gate,
-                                                     float *__restrict__ out, int n_fft, int d, int group_width, float t_new,
+                                                     float *__restrict__ partial, int n_fft, int d, int group_width, float t_new,
                                                      float t_old, int evict, int pos, float w32) {
     const int c = blockIdx.y * blockDim.x + threadIdx.x;
     if (c >= d) return;
@@ -72,53 +73,82 @@ __global__ void __launch_bounds__(256) decode_kernel(float2 *__restrict__ prefix
             acc += wgt * contrib;
         }
     }
-    if (MODE & 2) atomicAdd(out + c, acc / nf);
+    // deterministic read-out: every block leaves its partial sum, decode_reduce_kernel adds them in a fixed order
+    if (MODE & 2) partial[(size_t)blockIdx.x * d + c] = acc;
 }
 
+// out[c] = (sum over frequency chunks, in chunk order) / n_fft -- the fixed order makes the token bit-reproducible run to run
+__global__ void __launch_bounds__(256) decode_reduce_kernel(const float *__restrict__ partial, float *__restrict__ out, int nchunks, int d,
+                                                            float nf) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= d) return;
+    float acc = 0.f;
+    for (int i = 0; i < nchunks; ++i) acc += partial[(size_t)i * d + c];
+    out[c] = acc / nf;
+}
+
+int nchunks_of(int n_fft) { return (n_fft / 2 + 1 + kKChunk - 1) / kKChunk; }
+
 int launch(int mode, void *prefix, const float *v_new, const float *v_old, const void *gate, float *out, int n_fft, int d,
-           int group_width, long long t, int pos, cudaStream_t st) {
-    if (n_fft < 2 || d <= 0 || group_width <= 0 || (d % group_width) != 0) return SPECTRE_MIX_ERR_BAD_ARG;
+           int group_width, long long t, int pos, void *ws, size_t ws_bytes, cudaStream_t st) {
+    if (n_fft < 2 || d <= 0 || group_width <= 0 || (d % group_width) != 0)
+        return spx::fail(SPECTRE_MIX_ERR_BAD_ARG, "decode: bad size (n_fft=%d d=%d group_width=%d)", n_fft, d, group_width);
     const int F_half = n_fft / 2 + 1;
     const int threads = d >= 256 ? 256 : ((d + 31) / 32) * 32;
-    dim3 grid((F_half + kKChunk - 1) / kKChunk, (d + threads - 1) / threads);
+    const int nchunks = nchunks_of(n_fft);
+    dim3 grid(nchunks, (d + threads - 1) / threads);
+    (void)F_half;
     const float w32 = (float)(-2.0 * M_PI / (double)n_fft);
     const long long j = t % n_fft;
     const int evict = (t >= n_fft) ? 1 : 0;
-    if ((mode & 2) && out) {
-        cudaError_t e = cudaMemsetAsync(out, 0, sizeof(float) * (size_t)d, st);
-        if (e != cudaSuccess) return SPECTRE_MIX_ERR_CUDA + (int)e;
+    if (mode & 2) {
+        const size_t need = (size_t)nchunks * d * sizeof(float);
+        if (!ws || ws_bytes < need)
+            return spx::fail(SPECTRE_MIX_ERR_BAD_ARG, "decode: workspace %zu bytes given, spectre_decode_workspace_bytes() = %zu", ws ? ws_bytes : 0, need);
     }
     float2 *pf = reinterpret_cast<float2 *>(prefix);
     const float2 *g = reinterpret_cast<const float2 *>(gate);
+    float *part = reinterpret_cast<float *>(ws);
     switch (mode) {
-        case 1: decode_kernel<1><<<grid, threads, 0, st>>>(pf, v_new, v_old, g, out, n_fft, d, group_width, (float)t, (float)j, evict, pos, w32); break;
-        case 2: decode_kernel<2><<<grid, threads, 0, st>>>(pf, v_new, v_old, g, out, n_fft, d, group_width, (float)t, (float)j, evict, pos, w32); break;
-        default: decode_kernel<3><<<grid, threads, 0, st>>>(pf, v_new, v_old, g, out, n_fft, d, group_width, (float)t, (float)j, evict, pos, w32); break;
+        case 1: decode_kernel<1><<<grid, threads, 0, st>>>(pf, v_new, v_old, g, part, n_fft, d, group_width, (float)t, (float)j, evict, pos, w32); break;
+        case 2: decode_kernel<2><<<grid, threads, 0, st>>>(pf, v_new, v_old, g, part, n_fft, d, group_width, (float)t, (float)j, evict, pos, w32); break;
+        default: decode_kernel<3><<<grid, threads, 0, st>>>(pf, v_new, v_old, g, part, n_fft, d, group_width, (float)t, (float)j, evict, pos, w32); break;
     }
     cudaError_t e = cudaGetLastError();
-    return e == cudaSuccess ? 0 : SPECTRE_MIX_ERR_CUDA + (int)e;
+    if (e != cudaSuccess) return spx::cuda_fail(e, "decode kernel launch");
+    if (mode & 2) {
+        decode_reduce_kernel<<<(d + 255) / 256, 256, 0, st>>>(part, out, nchunks, d, (float)n_fft);
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return spx::cuda_fail(e, "decode reduce kernel launch");
+    }
+    return 0;
 }
 
 }  // namespace
 
 extern "C" {
 
+size_t spectre_decode_workspace_bytes(int n_fft, int d) {
+    if (n_fft < 2 || d <= 0) return 0;
+    return (size_t)nchunks_of(n_fft) * (size_t)d * sizeof(float);
+}
+
 int spectre_decode_update(void *prefix_fft, const float *v_new, const float *v_old, int n_fft, int d, long long t, void *stream) {
-    if (!prefix_fft || !v_new || (t >= n_fft && !v_old)) return SPECTRE_MIX_ERR_BAD_ARG;
-    return launch(1, prefix_fft, v_new, v_old, nullptr, nullptr, n_fft, d, 1, t, 0, reinterpret_cast<cudaStream_t>(stream));
+    if (!prefix_fft || !v_new || (t >= n_fft && !v_old)) return spx::fail(SPECTRE_MIX_ERR_BAD_ARG, "decode update: null pointer");
+    return launch(1, prefix_fft, v_new, v_old, nullptr, nullptr, n_fft, d, 1, t, 0, nullptr, 0, reinterpret_cast<cudaStream_t>(stream));
 }
 
 int spectre_decode_readout(const void *prefix_fft, const void *gate, float *out, int n_fft, int d, int group_width, int pos,
-                           void *stream) {
-    if (!prefix_fft || !gate || !out) return SPECTRE_MIX_ERR_BAD_ARG;
-    return launch(2, const_cast<void *>(prefix_fft), nullptr, nullptr, gate, out, n_fft, d, group_width, 0, pos,
-                  reinterpret_cast<cudaStream_t>(stream));
+                           void *workspace, size_t workspace_bytes, void *stream) {
+    if (!prefix_fft || !gate || !out) return spx::fail(SPECTRE_MIX_ERR_BAD_ARG, "decode readout: null pointer");
+    return launch(2, const_cast<void *>(prefix_fft), nullptr, nullptr, gate, out, n_fft, d, group_width, 0, pos, workspace,
+                  workspace_bytes, reinterpret_cast<cudaStream_t>(stream));
 }
 
 int spectre_decode_step(void *prefix_fft, const float *v_new, const float *v_old, const void *gate, float *out, int n_fft,
-                        int d, int group_width, long long t, void *stream) {
-    if (!prefix_fft || !v_new || !gate || !out || (t >= n_fft && !v_old)) return SPECTRE_MIX_ERR_BAD_ARG;
-    return launch(3, prefix_fft, v_new, v_old, gate, out, n_fft, d, group_width, t, (int)(t % n_fft),
+                        int d, int group_width, long long t, void *workspace, size_t workspace_bytes, void *stream) {
+    if (!prefix_fft || !v_new || !gate || !out || (t >= n_fft && !v_old)) return spx::fail(SPECTRE_MIX_ERR_BAD_ARG, "decode step: null pointer");
+    return launch(3, prefix_fft, v_new, v_old, gate, out, n_fft, d, group_width, t, (int)(t % n_fft), workspace, workspace_bytes,
                   reinterpret_cast<cudaStream_t>(stream));
 }
 

@@ -3,35 +3,76 @@
 // replacing, per head, interp_complex_1d (spectre.py:526-528 -> :26-61), ComplexModReLU (:531 -> :109-121) and the
 // positional phase (:534-536): about ten small PyTorch kernels per head and forward.
 #include <cuda_runtime.h>
+#include <math.h>
 #include <stdint.h>
+
+#include <algorithm>
 
 #include "../../include/spectre_mix.h"
 #include "spectre_gate.cuh"
+#include "spectre_internal.h"
 
 namespace {
 
-__global__ void __launch_bounds__(256) gate_expand_kernel(spx::GateSrc s, float2 *__restrict__ gate, int NG, int F_half) {
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    const int g = blockIdx.y, b = blockIdx.z;
-    if (k >= F_half) return;
-    const int head = g / s.G, j = g - head * s.G;
-    const float2 *a = s.anchors + ((size_t)b * NG + (size_t)head * s.G) * s.Bk;
-    const float2 *pos = s.pos ? s.pos + (size_t)b * s.pos_stride_b : nullptr;
-    gate[((size_t)b * NG + g) * F_half + k] =
-        spx::gate_from_anchors(a, s.Bk, s.G, j, k, F_half, __ldg(s.bias + (size_t)g * F_half + k), __ldg(s.eps + g), pos);
+// flat index over (b, g, k): no grid.y / grid.z limits, any B and NG the reference accepts
+// DECODE: multiply by the positional phase of SpectreHead.decode_step (spectre.py:594-598), exp(j theta_k) with
+// theta_k = fl(fl(fl(2 pi32 * k) * (t - j)) / n) -- complex64 tensor arithmetic of the reference, in its rounding order
+template <bool DECODE>
+__global__ void __launch_bounds__(256) gate_expand_kernel(spx::GateSrc s, float2 *__restrict__ gate, int NG, int F_half, long long total,
+                                                          float t_minus_j, float n_fft) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int k = (int)(i % F_half);
+        const long long r = i / F_half;
+        const int g = (int)(r % NG);
+        const long long b = r / NG;
+        const int head = g / s.G, j = g - head * s.G;
+        const float2 *a = s.anchors + ((size_t)b * NG + (size_t)head * s.G) * s.Bk;
+        const float2 *pos = s.pos ? s.pos + (size_t)b * s.pos_stride_b : nullptr;
+        float2 z = spx::gate_from_anchors(a, s.Bk, s.G, j, k, F_half, __ldg(s.bias + (size_t)g * F_half + k), __ldg(s.eps + g), pos);
+        if (DECODE) {
+            const float two_pi32 = (float)(2.0 * M_PI);
+            float sn, cs;
+            sincosf(__fdiv_rn(__fmul_rn(__fmul_rn(two_pi32, (float)k), t_minus_j), n_fft), &sn, &cs);
+            z = make_float2(z.x * cs - z.y * sn, z.x * sn + z.y * cs);
+        }
+        gate[i] = z;
+    }
 }
+
+int check_args(const void *anchors, const float *bias, const float *eps, void *gate, int B, int NG, int G, int Bk, int F_half) {
+    if (!anchors || !bias || !eps || !gate)
+        return spx::fail(SPECTRE_MIX_ERR_BAD_ARG, "gate expand: null pointer (anchors=%p bias=%p eps=%p gate=%p)", anchors, (const void *)bias,
+                         (const void *)eps, gate);
+    if (G <= 0 || NG <= 0 || NG % G != 0) return spx::fail(SPECTRE_MIX_ERR_BAD_ARG, "gate expand: NG=%d is not a positive multiple of G=%d", NG, G);
+    if (B < 0 || Bk < 1 || F_half < 2) return spx::fail(SPECTRE_MIX_ERR_BAD_ARG, "gate expand: bad size (B=%d Bk=%d F_half=%d)", B, Bk, F_half);
+    return 0;
+}
+
+int grid_for(long long total) { return (int)std::min<long long>((total + 255) / 256, 1 << 20); }
 
 }  // namespace
 
 extern "C" int spectre_gate_expand(const void *anchors, const float *bias, const float *eps, const void *pos_phase,
                                    long long pos_stride_b, void *gate, int B, int NG, int G, int Bk, int F_half, void *stream) {
-    if (!anchors || !bias || !eps || !gate) return SPECTRE_MIX_ERR_BAD_ARG;
-    if (G <= 0 || NG % G != 0) return SPECTRE_MIX_ERR_BAD_ARG;
-    if (B < 0 || NG <= 0 || Bk < 1 || F_half < 2 || NG > 65535 || B > 65535) return SPECTRE_MIX_ERR_BAD_ARG;
+    if (int rc = check_args(anchors, bias, eps, gate, B, NG, G, Bk, F_half)) return rc;
     if (B == 0) return 0;
     spx::GateSrc s{reinterpret_cast<const float2 *>(anchors), bias, eps, reinterpret_cast<const float2 *>(pos_phase), pos_stride_b, Bk, G};
-    dim3 grid((F_half + 255) / 256, NG, B);
-    gate_expand_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(s, reinterpret_cast<float2 *>(gate), NG, F_half);
+    const long long total = (long long)B * NG * F_half;
+    gate_expand_kernel<false><<<grid_for(total), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(s, reinterpret_cast<float2 *>(gate), NG, F_half,
+                                                                                                   total, 0.f, 1.f);
     cudaError_t e = cudaGetLastError();
-    return e == cudaSuccess ? 0 : SPECTRE_MIX_ERR_CUDA + (int)e;
+    return e == cudaSuccess ? 0 : spx::cuda_fail(e, "gate expand kernel launch");
+}
+
+extern "C" int spectre_decode_gate(const void *anchors, const float *bias, const float *eps, void *gate, int NG, int G, int Bk,
+                                   int F_half, long long t, int n_fft, void *stream) {
+    if (int rc = check_args(anchors, bias, eps, gate, 1, NG, G, Bk, F_half)) return rc;
+    if (n_fft < 2 || t < 0) return spx::fail(SPECTRE_MIX_ERR_BAD_ARG, "decode gate: bad n_fft=%d / t=%lld", n_fft, t);
+    spx::GateSrc s{reinterpret_cast<const float2 *>(anchors), bias, eps, nullptr, 0, Bk, G};
+    const long long total = (long long)NG * F_half;
+    const float tmj = (float)(t - t % n_fft);
+    gate_expand_kernel<true><<<grid_for(total), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(s, reinterpret_cast<float2 *>(gate), NG, F_half,
+                                                                                                  total, tmj, (float)n_fft);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : spx::cuda_fail(e, "decode gate kernel launch");
 }

@@ -11,6 +11,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cstdlib>
 #include <map>
 #include <mutex>
@@ -18,16 +19,15 @@
 #include <vector>
 
 #include "../../include/spectre_mix.h"
+#include "spectre_internal.h"
 #include "spectre_long.h"
 #include "spectre_mix_registry.h"
 
+namespace spx {
 namespace {
-
-using spx::KernelEntry;
-using spx::MixParams;
-
 thread_local std::string g_err;
-
+}
+// error reporting shared by every translation unit of the library (spectre_internal.h)
 int fail(int code, const char *fmt, ...) {
     char buf[512];
     va_list ap;
@@ -41,17 +41,28 @@ int cuda_fail(cudaError_t e, const char *what) {
     cudaGetLastError();  // clear the sticky-less error state
     return fail(SPECTRE_MIX_ERR_CUDA + (int)e, "%s: %s", what, cudaGetErrorString(e));
 }
+const char *last_error() { return g_err.c_str(); }
+}  // namespace spx
 
-int g_tile_channels_override = 0;
-int g_prefetch = 0;   // L2 prefetch of the next tiles: 0 off (default: the TMA unit is the busiest part of the TMEM variant), 1 TMA prefetch, 2 cooperative whole-line prefetch (needs -DSPX_COOP_PF=1)
-int g_use_tma = 1;
-int g_use_tmem = 1;
-int g_skew_ns = -350;   // warp stagger after the CTA barriers (see stagger() in the kernel header)
-int g_sched = 3;          // bit 0 stagger before the last inverse pass too, bit 1 split barrier around its read
-int g_use_two_pass = 1;
-int g_long_chunk_mb = 0;  // long-context path: rows per chunk sized so the intermediate stays in L2 (0 = whole batch at once)
-int g_l2_promo = 0;       // L2 promotion of the input tensor map: 0 none, 1 64 B, 2 128 B, 3 256 B
-unsigned long long *g_timeline = nullptr;
+namespace {
+
+using spx::cuda_fail;
+using spx::fail;
+using spx::KernelEntry;
+using spx::MixParams;
+
+// Tuning knobs (experiments / diagnostics only): process-wide atomics, read once per call with relaxed loads, so a call
+// always sees one consistent value of each and concurrent setters are not a data race.
+std::atomic<int> g_tile_channels_override{0};
+std::atomic<int> g_prefetch{0};   // L2 prefetch of the next tiles: 0 off (default: the TMA unit is the busiest part of the TMEM variant), 1 TMA prefetch, 2 cooperative whole-line prefetch (needs -DSPX_COOP_PF=1)
+std::atomic<int> g_use_tma{1};
+std::atomic<int> g_use_tmem{1};
+std::atomic<int> g_skew_ns{-350};   // warp stagger after the CTA barriers (see stagger() in the kernel header)
+std::atomic<int> g_sched{3};        // bit 0 stagger before the last inverse pass too, bit 1 split barrier around its read
+std::atomic<int> g_use_two_pass{1};
+std::atomic<int> g_long_chunk_mb{0};  // long-context path: rows per chunk sized so the intermediate stays in L2 (0 = whole batch at once)
+std::atomic<int> g_l2_promo{0};       // L2 promotion of the input tensor map: 0 none, 1 64 B, 2 128 B, 3 256 B
+std::atomic<unsigned long long *> g_timeline{nullptr};
 
 // ---------------------------------------------------------------- kernel registry
 const std::vector<KernelEntry> &registry() {
@@ -73,16 +84,27 @@ const std::vector<KernelEntry> &registry() {
 int mode_channels(int mode) { return mode == spx::MODE_QUAD ? 4 : (mode == spx::MODE_PAIR ? 2 : 1); }
 
 // ---------------------------------------------------------------- per-device state
+// Per-device state.  Nothing here is touched on the launch path except through lock-free reads: the device attributes are
+// filled once (std::call_once), a twiddle table is published through an atomic pointer once built (build + upload under the
+// device's mutex, first use of an n_fft only), the occupancy cache is a short critical section of its own.  Kernel launches
+// themselves run outside every lock, so host threads driving different streams never serialise on the library.
+constexpr int kMaxDevices = 64;
+constexpr int kMaxLog2N = 15;
 struct DeviceState {
+    std::once_flag once;
+    int init_rc = 0;
+    cudaError_t init_err = cudaSuccess;
     int sm_count = 0;
     int max_smem_optin = 0;
-    std::map<int, float2 *> twiddles;          // n_fft -> device table
-    void *scratch = nullptr;                   // long-context two-pass path: intermediate [B][R][4096][C] fp32
-    size_t scratch_bytes = 0;
-    std::map<std::pair<const KernelEntry *, int>, int> occupancy;  // (entry, gate_tables*2+has_mem) -> CTAs/SM
+    std::atomic<float2 *> twiddles[kMaxLog2N + 1] = {};   // log2(n_fft) -> device table (plain and SUB plans of one n_fft share it)
+    std::mutex mu;                                        // table creation, occupancy cache, pool creation
+    std::map<std::pair<const KernelEntry *, int>, int> occupancy;  // (entry, flags) -> CTAs/SM
+    // Scratch of the two-pass long-context path when the caller passes no workspace: stream-ordered allocations
+    // (cudaMallocFromPoolAsync / cudaFreeAsync on the CALLER's stream) from a private pool that keeps its memory, so calls on
+    // different streams can never share a buffer, nothing synchronises the device, and the pair is legal under stream capture.
+    std::atomic<cudaMemPool_t> pool{nullptr};
 };
-std::mutex g_mu;
-std::map<int, DeviceState> g_dev;
+DeviceState g_dev[kMaxDevices];
 
 // log2(x) when x is a power of two, else -1
 int ilog2_exact(int x) {
@@ -124,31 +146,63 @@ int get_device_state(DeviceState **out, int *dev_out) {
         cudaGetLastError();
         return fail(SPECTRE_MIX_ERR_NO_DEVICE, "no CUDA device: %s", cudaGetErrorString(e));
     }
+    if (dev < 0 || dev >= kMaxDevices) return fail(SPECTRE_MIX_ERR_NO_DEVICE, "device ordinal %d out of range", dev);
     DeviceState &st = g_dev[dev];
-    if (st.sm_count == 0) {
-        e = cudaDeviceGetAttribute(&st.sm_count, cudaDevAttrMultiProcessorCount, dev);
-        if (e != cudaSuccess) return cuda_fail(e, "cudaDeviceGetAttribute(SM count)");
-        e = cudaDeviceGetAttribute(&st.max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-        if (e != cudaSuccess) return cuda_fail(e, "cudaDeviceGetAttribute(smem optin)");
-    }
+    std::call_once(st.once, [&] {
+        st.init_err = cudaDeviceGetAttribute(&st.sm_count, cudaDevAttrMultiProcessorCount, dev);
+        if (st.init_err == cudaSuccess)
+            st.init_err = cudaDeviceGetAttribute(&st.max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    });
+    if (st.init_err != cudaSuccess) return cuda_fail(st.init_err, "cudaDeviceGetAttribute");
     *out = &st;
     if (dev_out) *dev_out = dev;
     return 0;
 }
 
 int get_twiddles(DeviceState &st, const KernelEntry &k, const float2 **tw) {
-    auto it = st.twiddles.find(k.n_fft);
-    if (it == st.twiddles.end()) {
-        std::vector<float2> h = build_twiddles(k.radix);
-        if ((int)h.size() != k.twn) return fail(SPECTRE_MIX_ERR_BAD_ARG, "internal: twiddle count %zu != %d", h.size(), k.twn);
-        float2 *d = nullptr;
-        cudaError_t e = cudaMalloc(&d, h.size() * sizeof(float2));
-        if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(twiddles)");
-        e = cudaMemcpy(d, h.data(), h.size() * sizeof(float2), cudaMemcpyHostToDevice);
-        if (e != cudaSuccess) return cuda_fail(e, "cudaMemcpy(twiddles)");
-        it = st.twiddles.emplace(k.n_fft, d).first;
+    int lg = 0;
+    while ((1 << lg) < k.n_fft) ++lg;
+    float2 *d = st.twiddles[lg].load(std::memory_order_acquire);
+    if (!d) {
+        // first use of this n_fft on this device: build in double on the host, upload (synchronous -- do one warm-up call
+        // before capturing a CUDA graph), publish.  Later calls take the lock-free path above.
+        std::lock_guard<std::mutex> lock(st.mu);
+        d = st.twiddles[lg].load(std::memory_order_acquire);
+        if (!d) {
+            std::vector<float2> h = build_twiddles(k.radix);
+            if ((int)h.size() != k.twn) return fail(SPECTRE_MIX_ERR_BAD_ARG, "internal: twiddle count %zu != %d", h.size(), k.twn);
+            cudaError_t e = cudaMalloc(&d, h.size() * sizeof(float2));
+            if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(twiddles)");
+            e = cudaMemcpy(d, h.data(), h.size() * sizeof(float2), cudaMemcpyHostToDevice);
+            if (e != cudaSuccess) { cudaFree(d); return cuda_fail(e, "cudaMemcpy(twiddles)"); }
+            st.twiddles[lg].store(d, std::memory_order_release);
+        }
     }
-    *tw = it->second;
+    *tw = d;
+    return 0;
+}
+
+// private stream-ordered pool of a device (created on first use, keeps what it allocated: release threshold = max)
+int get_pool(DeviceState &st, int dev, cudaMemPool_t *out) {
+    cudaMemPool_t p = st.pool.load(std::memory_order_acquire);
+    if (!p) {
+        std::lock_guard<std::mutex> lock(st.mu);
+        p = st.pool.load(std::memory_order_acquire);
+        if (!p) {
+            cudaMemPoolProps props;
+            memset(&props, 0, sizeof(props));
+            props.allocType = cudaMemAllocationTypePinned;
+            props.handleTypes = cudaMemHandleTypeNone;
+            props.location.type = cudaMemLocationTypeDevice;
+            props.location.id = dev;
+            cudaError_t e = cudaMemPoolCreate(&p, &props);
+            if (e != cudaSuccess) return cuda_fail(e, "cudaMemPoolCreate(long-context scratch pool)");
+            unsigned long long keep = ~0ull;
+            cudaMemPoolSetAttribute(p, cudaMemPoolAttrReleaseThreshold, &keep);
+            st.pool.store(p, std::memory_order_release);
+        }
+    }
+    *out = p;
     return 0;
 }
 
@@ -184,6 +238,7 @@ int pick_mode(int dtype, int group_width, const void *v, long long v_sb, long lo
 int choose(const DeviceState &st, int n_fft, int dtype, int mode_max, int C, int group_width, Choice *out,
            bool no_gate = false) {
     const std::vector<KernelEntry> &reg = registry();
+    const int g_tile_channels_override = ::g_tile_channels_override.load(std::memory_order_relaxed);
     // candidates in registry order (first = default) for the widest mode that has any variant
     for (int mode = mode_max; mode <= spx::MODE_REAL; ++mode) {
         const KernelEntry *best = nullptr;
@@ -234,6 +289,7 @@ int check_common(int B, int N, int n_fft, int C, int group_width) {
 
 int occupancy_of(DeviceState &st, const Choice &c, bool has_mem, bool tma, bool tmem = false) {
     auto key = std::make_pair(c.k, c.gate_tables * 8 + (has_mem ? 1 : 0) + (tma ? 2 : 0) + (tmem ? 4 : 0));
+    std::lock_guard<std::mutex> lock(st.mu);   // cache lookup only; the launch itself runs outside the lock
     auto it = st.occupancy.find(key);
     if (it != st.occupancy.end()) return it->second;
     int occ = c.k->occupancy(c.gate_tables, has_mem, tma, tmem);
@@ -323,10 +379,10 @@ int mix_two_pass_rows(DeviceState &st, const KernelEntry &k, const void *v, int 
     p.num_tiles = B * R * p.tiles_per_row;
     p.gate_tables = 2;                       // one full-length table = two half-length slots
     p.inv_n = 1.0f / (float)n_fft;
-    p.prefetch = g_prefetch;
+    p.prefetch = g_prefetch.load(std::memory_order_relaxed);
     p.timeline = nullptr;
-    p.skew_ns = g_skew_ns;
-    p.sched = g_sched;
+    p.skew_ns = g_skew_ns.load(std::memory_order_relaxed);
+    p.sched = g_sched.load(std::memory_order_relaxed);
     p.sub_R = R;
     p.sub_shift = ilog2_exact(R);
     p.gw_shift = ilog2_exact(group_width);
@@ -334,10 +390,12 @@ int mix_two_pass_rows(DeviceState &st, const KernelEntry &k, const void *v, int 
     c.k = &k;
     c.gate_tables = 2;
     alignas(64) CUtensorMap tmap, tmap_out;
-    bool tma = g_use_tma && k.tma_ok && (int)k.smem_bytes(2, true, false) <= st.max_smem_optin &&
-               make_v_tensor_map(&tmap, scr, SPECTRE_MIX_F32, p.v_sb, p.v_sn, B * R, sub, C, spx::kTmaBoxRows, tile_ch, g_l2_promo) &&
+    const bool use_tma = g_use_tma.load(std::memory_order_relaxed) != 0, use_tmem = g_use_tmem.load(std::memory_order_relaxed) != 0;
+    bool tma = use_tma && k.tma_ok && (int)k.smem_bytes(2, true, false) <= st.max_smem_optin &&
+               make_v_tensor_map(&tmap, scr, SPECTRE_MIX_F32, p.v_sb, p.v_sn, B * R, sub, C, spx::kTmaBoxRows, tile_ch,
+                                 g_l2_promo.load(std::memory_order_relaxed)) &&
                make_v_tensor_map(&tmap_out, scr, SPECTRE_MIX_F32, p.o_sb, p.o_sn, B * R, sub, C, k.out_box_rows, tile_ch);
-    const bool tmem = tma && g_use_tmem && k.tmem_ok && (int)k.smem_bytes(2, true, true) <= st.max_smem_optin;
+    const bool tmem = tma && use_tmem && k.tmem_ok && (int)k.smem_bytes(2, true, true) <= st.max_smem_optin;
     if (!tma && (int)k.smem_bytes(2, false, false) > st.max_smem_optin)
         return fail(SPECTRE_MIX_ERR_UNSUPPORTED, "internal: sub-transform kernel does not fit shared memory");
     const int occ = std::max(1, occupancy_of(st, c, mem != nullptr, tma, tmem));
@@ -350,96 +408,122 @@ int mix_two_pass_rows(DeviceState &st, const KernelEntry &k, const void *v, int 
     return 0;
 }
 
-// The batch is walked in chunks of rows whose complex intermediate (n_fft x C x 4 B per row) is small enough to stay in the
-// 126 MB L2 between the three launches: the intermediate is then written, transformed in place and read back without ever
-// reaching HBM (the same scratch lines are overwritten by the next chunk), so HBM sees V once and the output once.
-int mix_two_pass(DeviceState &st, const KernelEntry &k, const void *v, int dtype, long long v_sb, long long v_sn, const void *gate,
-                 const void *mem, long long mem_stride, void *out, long long o_sb, long long o_sn, int B, int n_io, int n_fft,
-                 int C, int group_width, cudaStream_t stream) {
+// rows of the batch one round of the three passes takes: the whole batch unless the L2-chunk experiment knob is set
+int two_pass_rows(int B, int n_fft, int C) {
     const size_t row_bytes = (size_t)n_fft * C * sizeof(float);
-    size_t chunk_mb = g_long_chunk_mb;
+    size_t chunk_mb = (size_t)g_long_chunk_mb.load(std::memory_order_relaxed);
     if (const char *env = getenv("SPECTRE_MIX_LONG_CHUNK_MB")) chunk_mb = (size_t)std::max(0L, strtol(env, nullptr, 10));   // experiment knob
-    int rows = chunk_mb == 0 ? B : (int)std::max<size_t>(1, std::min<size_t>((size_t)B, (chunk_mb << 20) / std::max<size_t>(row_bytes, 1)));
+    return chunk_mb == 0 ? B : (int)std::max<size_t>(1, std::min<size_t>((size_t)B, (chunk_mb << 20) / std::max<size_t>(row_bytes, 1)));
+}
+
+// does this call take the two-pass long-context path?  (QUAD layout, group width a multiple of 8, n_fft > 4096)
+const KernelEntry *two_pass_kernel(int n_fft, int mode, int group_width, const void *mem, long long mem_stride) {
+    if (!g_use_two_pass.load(std::memory_order_relaxed) || n_fft <= 4096 || mode != spx::MODE_QUAD || group_width % 8 != 0) return nullptr;
+    if (mem && (mem_stride % 2 != 0)) return nullptr;
+    return find_sub_kernel();
+}
+
+// The complex intermediate [rows][R][4096][C] fp32 lives in `ws` -- the caller's workspace when one was passed
+// (spectre_mix_fwd_ws), else a stream-ordered allocation from the device's private pool made on THIS call's stream, so two
+// calls on different streams never share a buffer (the round-1 per-device scratch did, and raced).  With the chunk knob the
+// batch is walked in chunks of rows whose intermediate is small enough to stay in the 126 MB L2 between the three launches.
+int mix_two_pass(DeviceState &st, int dev, const KernelEntry &k, const void *v, int dtype, long long v_sb, long long v_sn,
+                 const void *gate, const void *mem, long long mem_stride, void *out, long long o_sb, long long o_sn, int B, int n_io,
+                 int n_fft, int C, int group_width, void *ws, size_t ws_bytes, cudaStream_t stream) {
+    const size_t row_bytes = (size_t)n_fft * C * sizeof(float);
+    const int rows = two_pass_rows(B, n_fft, C);
     const size_t need = (size_t)rows * row_bytes;
-    if (need > st.scratch_bytes) {
-        if (st.scratch) cudaFree(st.scratch);
-        st.scratch = nullptr;
-        st.scratch_bytes = 0;
-        cudaError_t e = cudaMalloc(&st.scratch, need);
-        if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(long-context scratch)");
-        st.scratch_bytes = need;
+    float *scr = nullptr;
+    bool pooled = false;
+    if (ws) {
+        if (ws_bytes < need)
+            return fail(SPECTRE_MIX_ERR_BAD_ARG, "workspace too small: %zu bytes given, spectre_mix_workspace_bytes() = %zu", ws_bytes, need);
+        if (!aligned(ws, 16)) return fail(SPECTRE_MIX_ERR_UNSUPPORTED, "workspace must be 16-byte aligned");
+        scr = reinterpret_cast<float *>(ws);
+    } else {
+        cudaMemPool_t pool = nullptr;
+        if (int rc = get_pool(st, dev, &pool)) return rc;
+        void *pm = nullptr;
+        cudaError_t e = cudaMallocFromPoolAsync(&pm, need, pool, stream);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaMallocFromPoolAsync(long-context scratch)");
+        scr = reinterpret_cast<float *>(pm);
+        pooled = true;
     }
-    float *scr = reinterpret_cast<float *>(st.scratch);
     const size_t es = dtype == SPECTRE_MIX_F32 ? 4 : 2;
     const size_t gate_row = (size_t)(C / group_width) * (n_fft / 2 + 1) * sizeof(float2);
-    for (int b0 = 0; b0 < B; b0 += rows) {
+    int rc = 0;
+    for (int b0 = 0; b0 < B && !rc; b0 += rows) {
         const int nb = std::min(rows, B - b0);
-        int rc = mix_two_pass_rows(st, k, reinterpret_cast<const char *>(v) + (size_t)b0 * v_sb * es, dtype, v_sb, v_sn,
-                                   reinterpret_cast<const char *>(gate) + (size_t)b0 * gate_row, mem, mem_stride,
-                                   reinterpret_cast<char *>(out) + (size_t)b0 * o_sb * es, o_sb, o_sn, nb, n_io, n_fft, C, group_width,
-                                   scr, stream);
-        if (rc) return rc;
+        rc = mix_two_pass_rows(st, k, reinterpret_cast<const char *>(v) + (size_t)b0 * v_sb * es, dtype, v_sb, v_sn,
+                               reinterpret_cast<const char *>(gate) + (size_t)b0 * gate_row, mem, mem_stride,
+                               reinterpret_cast<char *>(out) + (size_t)b0 * o_sb * es, o_sb, o_sn, nb, n_io, n_fft, C, group_width,
+                               scr, stream);
     }
-    return 0;
+    if (pooled) {
+        cudaError_t e = cudaFreeAsync(scr, stream);   // stream-ordered: the memory goes back to the pool after the post pass
+        if (e != cudaSuccess && !rc) rc = cuda_fail(e, "cudaFreeAsync(long-context scratch)");
+    }
+    return rc;
 }
 
 }  // namespace
 
 extern "C" {
 
-int spectre_mix_abi_version(void) { return 1; }
+int spectre_mix_abi_version(void) { return 2; }
 
-const char *spectre_mix_last_error(void) { return g_err.c_str(); }
+const char *spectre_mix_last_error(void) { return spx::last_error(); }
 
 int spectre_mix_set_tile_channels(int tile_channels) {
     if (tile_channels < 0) return fail(SPECTRE_MIX_ERR_BAD_ARG, "tile_channels < 0");
-    g_tile_channels_override = tile_channels;
+    g_tile_channels_override.store(tile_channels);
     return 0;
 }
 
 int spectre_mix_set_prefetch(int enable) {
-    g_prefetch = enable < 0 ? 0 : enable;   // 0 off, 1 TMA prefetch of the next tiles, 2 cooperative whole-line prefetch (TMEM variant)
+    g_prefetch.store(enable < 0 ? 0 : enable);   // 0 off, 1 TMA prefetch of the next tiles, 2 cooperative whole-line prefetch (TMEM variant)
     return 0;
 }
 
 int spectre_mix_set_timeline(void *device_buffer) {
-    g_timeline = reinterpret_cast<unsigned long long *>(device_buffer);
+    g_timeline.store(reinterpret_cast<unsigned long long *>(device_buffer));
     return 0;
 }
 
 int spectre_mix_set_two_pass(int enable) {
-    g_use_two_pass = enable ? 1 : 0;
+    g_use_two_pass.store(enable ? 1 : 0);
     return 0;
 }
 
 int spectre_mix_set_skew_ns(int code) {
-    g_skew_ns = code;
+    g_skew_ns.store(code);
     return 0;
 }
 
 int spectre_mix_set_l2_promotion(int level) {
-    g_l2_promo = level < 0 ? 0 : (level > 3 ? 3 : level);
+    g_l2_promo.store(level < 0 ? 0 : (level > 3 ? 3 : level));
     return 0;
 }
 
 int spectre_mix_set_sched(int flags) {
-    g_sched = flags;
+    g_sched.store(flags);
     return 0;
 }
 
 int spectre_mix_set_tmem(int enable) {
-    g_use_tmem = enable ? 1 : 0;
+    g_use_tmem.store(enable ? 1 : 0);
     return 0;
 }
 
 int spectre_mix_set_tma(int enable) {
-    g_use_tma = enable ? 1 : 0;
+    g_use_tma.store(enable ? 1 : 0);
     return 0;
 }
 
-int spectre_mix_fwd(const void *v, int v_dtype, int64_t v_stride_b, int64_t v_stride_n, const void *gate,
-                    const void *mem, int64_t mem_stride, void *out, int out_dtype, int64_t out_stride_b,
-                    int64_t out_stride_n, int B, int N, int n_fft, int C, int group_width, void *stream) {
+namespace {
+int mix_fwd_impl(const void *v, int v_dtype, int64_t v_stride_b, int64_t v_stride_n, const void *gate, const void *mem,
+                 int64_t mem_stride, void *out, int out_dtype, int64_t out_stride_b, int64_t out_stride_n, int B, int N, int n_fft,
+                 int C, int group_width, void *ws, size_t ws_bytes, void *stream) {
     if (int rc = check_common(B, N, n_fft, C, group_width)) return rc;
     if (v_dtype != out_dtype || (v_dtype != SPECTRE_MIX_F32 && v_dtype != SPECTRE_MIX_BF16))
         return fail(SPECTRE_MIX_ERR_UNSUPPORTED, "dtype pair (%d, %d) unsupported: V and out must both be f32 or both bf16",
@@ -451,18 +535,16 @@ int spectre_mix_fwd(const void *v, int v_dtype, int64_t v_stride_b, int64_t v_st
     if (mem && !aligned(mem, 8)) return fail(SPECTRE_MIX_ERR_UNSUPPORTED, "memory must be 8-byte aligned");
     if (mem && mem_stride < C) return fail(SPECTRE_MIX_ERR_BAD_ARG, "mem_stride=%lld < C=%d", (long long)mem_stride, C);
 
-    std::lock_guard<std::mutex> lock(g_mu);
     DeviceState *st = nullptr;
-    if (int rc = get_device_state(&st, nullptr)) return rc;
+    int dev = 0;
+    if (int rc = get_device_state(&st, &dev)) return rc;
 
     const int mode = pick_mode(v_dtype, group_width, v, v_stride_b, v_stride_n, out, out_stride_b, out_stride_n, mem,
                                mem_stride);
     // long transforms: one streaming radix-R pass, R interleaved 4096-point transforms in shared memory, one streaming pass
-    if (g_use_two_pass && n_fft > 4096 && mode == spx::MODE_QUAD && group_width % 8 == 0 && (!mem || (mem_stride % 2 == 0))) {
-        if (const KernelEntry *ks = find_sub_kernel())
-            return mix_two_pass(*st, *ks, v, v_dtype, v_stride_b, v_stride_n, gate, mem, mem_stride, out, out_stride_b,
-                                out_stride_n, B, n_io, n_fft, C, group_width, reinterpret_cast<cudaStream_t>(stream));
-    }
+    if (const KernelEntry *ks = two_pass_kernel(n_fft, mode, group_width, mem, mem_stride))
+        return mix_two_pass(*st, dev, *ks, v, v_dtype, v_stride_b, v_stride_n, gate, mem, mem_stride, out, out_stride_b,
+                            out_stride_n, B, n_io, n_fft, C, group_width, ws, ws_bytes, reinterpret_cast<cudaStream_t>(stream));
     Choice c;
     if (int rc = choose(*st, n_fft, v_dtype, mode, C, group_width, &c)) return rc;
     const float2 *tw = nullptr;
@@ -490,10 +572,10 @@ int spectre_mix_fwd(const void *v, int v_dtype, int64_t v_stride_b, int64_t v_st
     p.num_tiles = B * c.tiles_per_row;
     p.gate_tables = c.gate_tables;
     p.inv_n = 1.0f / (float)n_fft;
-    p.prefetch = g_prefetch;
-    p.timeline = g_timeline;
-    p.skew_ns = g_skew_ns;
-    p.sched = g_sched;
+    p.prefetch = g_prefetch.load(std::memory_order_relaxed);
+    p.timeline = g_timeline.load(std::memory_order_relaxed);
+    p.skew_ns = g_skew_ns.load(std::memory_order_relaxed);
+    p.sched = g_sched.load(std::memory_order_relaxed);
     p.sub_R = 1;
     p.sub_shift = 0;
     p.gw_shift = ilog2_exact(group_width);
@@ -501,12 +583,13 @@ int spectre_mix_fwd(const void *v, int v_dtype, int64_t v_stride_b, int64_t v_st
     // TMA-fed variant when V's layout can be described to the TMA unit; otherwise direct 128-bit global loads
     alignas(64) CUtensorMap tmap, tmap_out;
     const int tile_ch = mode_channels(c.k->mode) * c.k->ncol;
-    bool tma = g_use_tma && c.k->tma_ok && (int)c.k->smem_bytes(c.gate_tables, true, false) <= st->max_smem_optin &&
+    const bool use_tma = g_use_tma.load(std::memory_order_relaxed) != 0, use_tmem = g_use_tmem.load(std::memory_order_relaxed) != 0;
+    bool tma = use_tma && c.k->tma_ok && (int)c.k->smem_bytes(c.gate_tables, true, false) <= st->max_smem_optin &&
                tma_layout_ok(v, v_dtype, v_stride_b, v_stride_n) && tma_layout_ok(out, out_dtype, out_stride_b, out_stride_n) &&
                make_v_tensor_map(&tmap, v, v_dtype, v_stride_b, v_stride_n, B, n_io, C, std::min(n_fft, spx::kTmaBoxRows),
-                                 tile_ch, g_l2_promo) &&
+                                 tile_ch, g_l2_promo.load(std::memory_order_relaxed)) &&
                make_v_tensor_map(&tmap_out, out, out_dtype, out_stride_b, out_stride_n, B, n_io, C, c.k->out_box_rows, tile_ch);
-    const bool tmem = tma && g_use_tmem && c.k->tmem_ok && (int)c.k->smem_bytes(c.gate_tables, true, true) <= st->max_smem_optin;
+    const bool tmem = tma && use_tmem && c.k->tmem_ok && (int)c.k->smem_bytes(c.gate_tables, true, true) <= st->max_smem_optin;
     const int occ = std::max(1, occupancy_of(*st, c, mem != nullptr, tma, tmem));
     const int grid = std::min(p.num_tiles, st->sm_count * occ);
     cudaError_t e = c.k->launch(p, grid, mem != nullptr, tma ? &tmap : nullptr, tma ? &tmap_out : nullptr, tmem,
@@ -514,17 +597,45 @@ int spectre_mix_fwd(const void *v, int v_dtype, int64_t v_stride_b, int64_t v_st
     if (e != cudaSuccess) return cuda_fail(e, "kernel launch");
     return 0;
 }
+}  // namespace
+
+int spectre_mix_fwd(const void *v, int v_dtype, int64_t v_stride_b, int64_t v_stride_n, const void *gate,
+                    const void *mem, int64_t mem_stride, void *out, int out_dtype, int64_t out_stride_b,
+                    int64_t out_stride_n, int B, int N, int n_fft, int C, int group_width, void *stream) {
+    return mix_fwd_impl(v, v_dtype, v_stride_b, v_stride_n, gate, mem, mem_stride, out, out_dtype, out_stride_b, out_stride_n, B, N,
+                        n_fft, C, group_width, nullptr, 0, stream);
+}
+
+int spectre_mix_fwd_ws(const void *v, int v_dtype, int64_t v_stride_b, int64_t v_stride_n, const void *gate,
+                       const void *mem, int64_t mem_stride, void *out, int out_dtype, int64_t out_stride_b,
+                       int64_t out_stride_n, int B, int N, int n_fft, int C, int group_width, void *workspace,
+                       size_t workspace_bytes, void *stream) {
+    if (!workspace && workspace_bytes) return fail(SPECTRE_MIX_ERR_BAD_ARG, "workspace is null but workspace_bytes = %zu", workspace_bytes);
+    return mix_fwd_impl(v, v_dtype, v_stride_b, v_stride_n, gate, mem, mem_stride, out, out_dtype, out_stride_b, out_stride_n, B, N,
+                        n_fft, C, group_width, workspace, workspace_bytes, stream);
+}
+
+size_t spectre_mix_workspace_bytes(int v_dtype, int B, int N, int n_fft, int C, int group_width) {
+    (void)v_dtype;
+    if (check_common(B, N, n_fft, C, group_width)) return 0;
+    if (B == 0 || C == 0 || std::min(N, n_fft) == 0) return 0;
+    // upper bound over layouts: the two-pass path is taken when the tensors allow the packed (QUAD) layout; a call that
+    // falls back to a single-kernel variant ignores the workspace
+    const int mode = (group_width % 4 == 0) ? spx::MODE_QUAD : ((group_width % 2 == 0) ? spx::MODE_PAIR : spx::MODE_REAL);
+    if (!two_pass_kernel(n_fft, mode, group_width, nullptr, 0)) return 0;
+    return (size_t)two_pass_rows(B, n_fft, C) * (size_t)n_fft * C * sizeof(float);
+}
 
 int spectre_mix_plan(int v_dtype, int out_dtype, int has_mem, int B, int N, int n_fft, int C, int group_width,
                      spectre_mix_plan_info *info) {
     if (!info) return fail(SPECTRE_MIX_ERR_BAD_ARG, "info is null");
     if (int rc = check_common(B, N, n_fft, C, group_width)) return rc;
     if (v_dtype != out_dtype) return fail(SPECTRE_MIX_ERR_UNSUPPORTED, "dtype pair unsupported");
-    std::lock_guard<std::mutex> lock(g_mu);
     DeviceState *st = nullptr;
     if (int rc = get_device_state(&st, nullptr)) return rc;
     const int mode = (group_width % 4 == 0) ? spx::MODE_QUAD : ((group_width % 2 == 0) ? spx::MODE_PAIR : spx::MODE_REAL);
-    const KernelEntry *ks = (g_use_two_pass && n_fft > 4096 && mode == spx::MODE_QUAD && group_width % 8 == 0) ? find_sub_kernel() : nullptr;
+    const KernelEntry *ks = two_pass_kernel(n_fft, mode, group_width, nullptr, 0);
+    const bool g_use_tma = ::g_use_tma.load(std::memory_order_relaxed) != 0, g_use_tmem = ::g_use_tmem.load(std::memory_order_relaxed) != 0;
     Choice c;
     if (ks) {
         c.k = ks;
@@ -541,6 +652,7 @@ int spectre_mix_plan(int v_dtype, int out_dtype, int has_mem, int B, int N, int 
     info->grid = std::min(B * (ks ? n_fft / 4096 : 1) * c.tiles_per_row, st->sm_count * info->ctas_per_sm);
     info->launches = ks ? 3 : 1;   // long transforms: pre pass + 4096-point sub-transforms + post pass
     info->algorithmic_bytes = algorithmic_bytes(v_dtype, has_mem != 0, B, N, n_fft, C, group_width);
+    info->workspace_bytes = (int64_t)spectre_mix_workspace_bytes(v_dtype, B, N, n_fft, C, group_width);
     return 0;
 }
 
@@ -552,7 +664,6 @@ int spectre_rfft_fwd(const void *v, int v_dtype, int64_t v_stride_b, int64_t v_s
     if (B == 0 || C == 0) return 0;
     if (!spec || (!v && N > 0)) return fail(SPECTRE_MIX_ERR_BAD_ARG, "null pointer");
     if (!aligned(spec, 8)) return fail(SPECTRE_MIX_ERR_UNSUPPORTED, "spec must be 8-byte aligned");
-    std::lock_guard<std::mutex> lock(g_mu);
     DeviceState *st = nullptr;
     if (int rc = get_device_state(&st, nullptr)) return rc;
     Choice c;
@@ -594,7 +705,8 @@ constexpr int kHostStreams = 4;   // chunks in flight: H2D of one, kernel of ano
 struct HostCtx {
     cudaStream_t s[kHostStreams] = {};
     void *dv[kHostStreams] = {}, *dg[kHostStreams] = {}, *dout[kHostStreams] = {};
-    size_t cap_v = 0, cap_g = 0;
+    void *dws[kHostStreams] = {};   // long-context workspace, one per stream: chunks in flight never share an intermediate
+    size_t cap_v = 0, cap_g = 0, cap_ws = 0;
     void *dmem = nullptr;
     size_t cap_mem = 0;
 };
@@ -648,6 +760,15 @@ int spectre_mix_fwd_host(const float *v, const float *gate, const float *mem, fl
         }
         h.cap_g = need_g;
     }
+    const size_t need_ws = spectre_mix_workspace_bytes(SPECTRE_MIX_F32, rows, N, n_fft, C, group_width);
+    if (need_ws > h.cap_ws) {
+        for (int i = 0; i < kHostStreams; ++i) {
+            cudaFree(h.dws[i]);   // every stream was synchronised when the previous call returned
+            h.dws[i] = nullptr;
+            if ((e = cudaMalloc(&h.dws[i], need_ws)) != cudaSuccess) { h.cap_ws = 0; return cuda_fail(e, "cudaMalloc(long-context workspace)"); }
+        }
+        h.cap_ws = need_ws;
+    }
     if (mem) {
         const size_t need_m = fh * (size_t)C * 8;
         if (need_m > h.cap_mem) {
@@ -669,8 +790,9 @@ int spectre_mix_fwd_host(const float *v, const float *gate, const float *mem, fl
         if ((e = cudaMemcpyAsync(h.dg[i], reinterpret_cast<const char *>(gate) + (size_t)b0 * row_g, row_g * nb,
                                  cudaMemcpyHostToDevice, s)) != cudaSuccess)
             return cuda_fail(e, "H2D gate");
-        int rc = spectre_mix_fwd(h.dv[i], SPECTRE_MIX_F32, (int64_t)N * C, C, h.dg[i], mem ? h.dmem : nullptr, C, h.dout[i],
-                                 SPECTRE_MIX_F32, (int64_t)n_io * C, C, nb, N, n_fft, C, group_width, s);
+        int rc = spectre_mix_fwd_ws(h.dv[i], SPECTRE_MIX_F32, (int64_t)N * C, C, h.dg[i], mem ? h.dmem : nullptr, C, h.dout[i],
+                                    SPECTRE_MIX_F32, (int64_t)n_io * C, C, nb, N, n_fft, C, group_width,
+                                    need_ws ? h.dws[i] : nullptr, need_ws ? h.cap_ws : 0, s);
         if (rc) return rc;
         if ((e = cudaMemcpyAsync(out + (size_t)b0 * n_io * C, h.dout[i], row_o * nb, cudaMemcpyDeviceToHost, s)) !=
             cudaSuccess)

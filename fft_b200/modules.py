@@ -156,9 +156,11 @@ class WaveletRefinement(nn.Module):
 
     def forward(self, v: torch.Tensor, q_pool: torch.Tensor) -> torch.Tensor:
         B = v.shape[0]
-        if self.on_rate <= 0.0:
-            return v          # rand() < 0 never fires: skip the mask and the host sync of `on.any()` below
+        # spectre.py:841 always draws the mask: draw it too, so the global RNG stream (e.g. later dropout masks) stays in
+        # step with the reference under the same seed; only the host sync of `on.any()` is skipped when it cannot fire
         on = torch.rand(B, 1, 1, device=v.device) < self.on_rate
+        if self.on_rate <= 0.0:
+            return v
         if not on.any():
             return v
         gate = self.gate_mlp(q_pool).unsqueeze(1)
@@ -213,20 +215,12 @@ def head_forward(head, x, pos_phase=None, return_q_pool=False, memory_fft=None):
 def _stacked(mh, path: str) -> torch.Tensor:
     """Per-head parameter `path` (e.g. ``"gate_mlp.0.weight"``) of every head stacked along a new leading axis.
 
-    The heads keep their own parameters (state_dict parity with spectre.py:677-690); the stack is rebuilt when
-    gradients are needed and cached on the module (keyed by storage and version counters) otherwise.
+    The heads keep their own parameters (state_dict parity with spectre.py:677-690) and the stack is rebuilt from the LIVE
+    parameters on every call, as the reference reads them: no cache that an in-place ``p.data.copy_(ema)`` (which bumps
+    neither ``data_ptr`` nor the version counter) could leave stale.  It is H small tensors -- one ``cat`` kernel.
     """
     ps = [h.get_parameter(path) if path.rsplit(".", 1)[-1] != "eps" else h.get_buffer(path) for h in mh.heads]
-    if torch.is_grad_enabled() and any(p.requires_grad for p in ps):
-        return torch.stack(ps, dim=0)
-    cache = mh.__dict__.setdefault("_spx_stacks", {})
-    key = tuple((p.data_ptr(), p._version) for p in ps)
-    hit = cache.get(path)
-    if hit is None or hit[0] != key:
-        with torch.no_grad():
-            hit = (key, torch.stack([p.detach() for p in ps], dim=0))
-        cache[path] = hit
-    return hit[1]
+    return torch.stack(ps, dim=0)
 
 
 def _mean_like(pooling) -> bool:
@@ -284,7 +278,7 @@ def multihead_forward(mh, x, pos_phase=None, memory_fft=None):
     H = mh.num_heads
     h0 = mh.heads[0]
     B, N, d = x.shape
-    xh = x.view(B, N, H, d // H)
+    xh = x.unflatten(-1, (H, d // H))   # any strides, like the torch.chunk of spectre.py:703
     V_all = torch.einsum("bnhi,hoi->bnho", xh, _stacked(mh, "W_v.weight")).reshape(B, N, d)   # head h = channels [h*d_h, (h+1)*d_h)
     Q_all = torch.einsum("bnhi,hoi->bnho", xh, _stacked(mh, "W_q.weight"))                    # (B, N, H, d_h)
     if x.is_cuda and _heads_batchable(mh):

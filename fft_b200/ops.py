@@ -60,12 +60,16 @@ def _mix_impl(V: torch.Tensor, gate: torch.Tensor, memory: Optional[torch.Tensor
         return out
     lib = _lib.load()
     with torch.cuda.device(V.device):
+        # scratch of the long-context path (n_fft > 4096) comes from torch's caching allocator: owned by this call's
+        # stream, safe with side streams and under CUDA-graph capture (the kernel never allocates)
+        ws_bytes = lib.spectre_mix_workspace_bytes(_DT[V.dtype], B, N, n_fft, C, group_width)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=V.device) if ws_bytes else None
         stream = torch.cuda.current_stream(V.device).cuda_stream
-        rc = lib.spectre_mix_fwd(
+        rc = lib.spectre_mix_fwd_ws(
             V.data_ptr(), _DT[V.dtype], V.stride(0), V.stride(1),
             gate.data_ptr(), mem_ptr, mem_stride,
             out.data_ptr(), _DT[out.dtype], out.stride(0), out.stride(1),
-            B, N, n_fft, C, group_width, ctypes.c_void_p(stream),
+            B, N, n_fft, C, group_width, ws.data_ptr() if ws is not None else None, ws_bytes, ctypes.c_void_p(stream),
         )
     _lib.check(rc, "spectral_mix")
     return out
@@ -274,14 +278,27 @@ def spectral_mix_host(V: torch.Tensor, gate: torch.Tensor, memory: Optional[torc
     """
     if V.is_cuda or gate.is_cuda:
         raise RuntimeError("spectral_mix_host takes CPU tensors; use spectral_mix for CUDA tensors")
+    if V.dim() != 3:
+        raise ValueError(f"V must be (B, N, C), got {tuple(V.shape)}")
     V = V.contiguous().float()
     gate = gate.contiguous().to(torch.complex64)
     B, N, C = V.shape
     n_out = min(N, n_fft)
+    F_half = n_fft // 2 + 1
+    if group_width <= 0 or C % group_width:
+        raise ValueError(f"C={C} is not a multiple of group_width={group_width}")
+    if tuple(gate.shape) != (B, C // group_width, F_half):
+        raise ValueError(f"gate must be {(B, C // group_width, F_half)}, got {tuple(gate.shape)}")
     if out is None:
         out = torch.empty((B, n_out, C), dtype=torch.float32)
+    elif (out.is_cuda or out.dtype != torch.float32 or tuple(out.shape) != (B, n_out, C) or not out.is_contiguous()):
+        # the C entry writes B * n_out * C floats through this pointer: anything else would be an out-of-bounds write
+        raise ValueError(f"out must be a contiguous CPU float32 tensor of shape {(B, n_out, C)}, got "
+                         f"{tuple(out.shape)} {out.dtype} on {out.device} (contiguous={out.is_contiguous()})")
     mem_ptr = None
     if memory is not None:
+        if tuple(memory.shape) != (F_half, C):
+            raise ValueError(f"memory must be {(F_half, C)}, got {tuple(memory.shape)}")
         memory = memory.contiguous().to(torch.complex64)
         mem_ptr = memory.data_ptr()
     lib = _lib.load()
@@ -301,4 +318,5 @@ def plan_info(B: int, N: int, n_fft: int, C: int, group_width: int, dtype: torch
         "n_fft": info.n_fft, "radix": [r for r in info.radix if r > 1], "tile_channels": info.tile_channels,
         "threads": info.threads, "ctas_per_sm": info.ctas_per_sm, "smem_bytes": info.smem_bytes,
         "grid": info.grid, "launches": info.launches, "algorithmic_bytes": info.algorithmic_bytes,
+        "workspace_bytes": info.workspace_bytes,
     }

@@ -16,11 +16,18 @@
  * head h are rows [h*G, (h+1)*G) of `gate`, group_width = head_dim / G.
  *
  * Threading / ownership: the caller owns every buffer; calls are asynchronous on
- * `stream` (device entry points) and never synchronise the device; per-device
- * twiddle tables are created on first use under a mutex and are safe to use
- * from several host threads and under CUDA-graph capture after one warm-up call.
- * There is no CPU fallback and no cuFFT: an unsupported argument returns an
- * error code and sets spectre_mix_last_error().
+ * `stream` (device entry points) and never synchronise the device.  The only
+ * library-owned device memory is (a) one twiddle table per (device, n_fft),
+ * built and uploaded on the FIRST call with that n_fft (a synchronous copy: make
+ * one warm-up call before capturing a CUDA graph), read lock-free afterwards,
+ * and (b) for callers of spectre_mix_fwd that pass no workspace at
+ * n_fft > 4096, a stream-ordered allocation (cudaMallocFromPoolAsync /
+ * cudaFreeAsync on the caller's stream, private pool) per call -- never shared
+ * between streams, legal under stream capture.  Pass a workspace
+ * (spectre_mix_workspace_bytes + spectre_mix_fwd_ws) to own that memory too.
+ * Launches take no lock: host threads driving different streams do not
+ * serialise on the library.  There is no CPU fallback and no cuFFT: an
+ * unsupported argument returns an error code and sets spectre_mix_last_error().
  */
 #ifndef SPECTRE_MIX_H_
 #define SPECTRE_MIX_H_
@@ -65,6 +72,20 @@ int spectre_mix_fwd(const void *v, int v_dtype, int64_t v_stride_b, int64_t v_st
                     void *out, int out_dtype, int64_t out_stride_b, int64_t out_stride_n,
                     int B, int N, int n_fft, int C, int group_width, void *stream);
 
+/* Scratch the call needs for the given problem (bytes; 0 for every n_fft <= 4096 and for layouts that run as a
+ * single kernel).  n_fft = 8192 / 16384 with a packed layout run as three launches around a complex intermediate
+ * [B][n_fft][C] fp32 that lives in the workspace (the kernel never allocates). */
+size_t spectre_mix_workspace_bytes(int v_dtype, int B, int N, int n_fft, int C, int group_width);
+
+/* spectre_mix_fwd with caller-owned scratch: `workspace` = device memory of at least spectre_mix_workspace_bytes(...)
+ * bytes, 16-byte aligned, used only by this call's launches on `stream` (so one workspace per stream in flight).
+ * workspace = NULL behaves like spectre_mix_fwd (stream-ordered internal allocation when scratch is needed). */
+int spectre_mix_fwd_ws(const void *v, int v_dtype, int64_t v_stride_b, int64_t v_stride_n,
+                       const void *gate, const void *mem, int64_t mem_stride,
+                       void *out, int out_dtype, int64_t out_stride_b, int64_t out_stride_n,
+                       int B, int N, int n_fft, int C, int group_width,
+                       void *workspace, size_t workspace_bytes, void *stream);
+
 /* Same function on HOST buffers (what a non-CUDA host language binds): copies
  * v/gate/mem to the device in batch chunks, runs the kernel and copies the
  * result back, overlapping the three on internal streams; returns when `out`
@@ -88,12 +109,23 @@ int spectre_rfft_fwd(const void *v, int v_dtype, int64_t v_stride_b, int64_t v_s
  * spectre_decode_readout  replaces `gate_broadcast * prefix_fft` + pruned_irfft_single, spectre.py:605, :614-655;
  *                         gate = complex64 [d/group_width][n_fft/2+1] (already multiplied by the positional phase of
  *                         spectre.py:594-598), out = float32 [d], pos = output sample index
- * spectre_decode_step     both in one pass: update with (v_new, v_old, t), then read sample t % n_fft out */
+ * spectre_decode_step     both in one pass: update with (v_new, v_old, t), then read sample t % n_fft out
+ * The read-out reduces over frequency in two stages (per-block partial sums in `workspace`, then a fixed-order sum), so a
+ * token is bit-reproducible run to run like the reference's `sum(dim=0)`; workspace = device memory of
+ * spectre_decode_workspace_bytes(n_fft, d) bytes, owned by the caller (one per cache). */
+size_t spectre_decode_workspace_bytes(int n_fft, int d);
 int spectre_decode_update(void *prefix_fft, const float *v_new, const float *v_old, int n_fft, int d, long long t, void *stream);
 int spectre_decode_readout(const void *prefix_fft, const void *gate, float *out, int n_fft, int d, int group_width, int pos,
-                           void *stream);
+                           void *workspace, size_t workspace_bytes, void *stream);
 int spectre_decode_step(void *prefix_fft, const float *v_new, const float *v_old, const void *gate, float *out, int n_fft,
-                        int d, int group_width, long long t, void *stream);
+                        int d, int group_width, long long t, void *workspace, size_t workspace_bytes, void *stream);
+
+/* Gate of SpectreHead.decode_step (spectre.py:586-598) in ONE launch: cubic interpolation of the anchors, modReLU and the
+ * decode-time positional phase exp(j * 2 pi k (t - t % n_fft) / n_fft), the angle evaluated in float32 in the reference's
+ * rounding order.  anchors complex64 [NG][Bk] (gate_mlp output of the running descriptor), bias [NG][F_half], eps [NG],
+ * gate complex64 [NG][F_half]; G = gate rows per head as in spectre_gate_expand. */
+int spectre_decode_gate(const void *anchors, const float *bias, const float *eps, void *gate, int NG, int G, int Bk,
+                        int F_half, long long t, int n_fft, void *stream);
 
 /* ---- gate generator tail: for ALL heads of a layer in one launch,
  *   gate[b, g, k] = modReLU_g( cubic_interp(planes of anchors[b, head(g)])(k) ) * pos_phase[b or 0, k]
@@ -121,6 +153,7 @@ typedef struct spectre_mix_plan_info {
     int grid;              /* CTAs launched for the given problem */
     int launches;          /* kernel launches per call */
     int64_t algorithmic_bytes; /* V + out + gate (+ mem) bytes of the call */
+    int64_t workspace_bytes;   /* = spectre_mix_workspace_bytes(...) */
 } spectre_mix_plan_info;
 
 int spectre_mix_plan(int v_dtype, int out_dtype, int has_mem, int B, int N, int n_fft, int C,
@@ -129,7 +162,7 @@ int spectre_mix_plan(int v_dtype, int out_dtype, int has_mem, int B, int N, int 
 /* Override the tile width (channels per CTA; 0 = automatic).  For experiments only. */
 int spectre_mix_set_tile_channels(int tile_channels);
 
-/* Enable (default) / disable the L2 prefetch of a CTA's next tile.  For experiments only. */
+/* L2 prefetch of a CTA's next tiles: 0 off (default), 1 TMA prefetch, 2 cooperative whole-line prefetch (diagnostic build).  For experiments only. */
 int spectre_mix_set_prefetch(int enable);
 
 /* Enable (default) / disable TMA-staged tile loads (falls back to direct 128-bit global loads).  For experiments only. */

@@ -36,7 +36,7 @@ def test_header_symbols_are_exported(lib):
 
 def test_abi_version_and_error_string(lib):
     lib.spectre_mix_abi_version.restype = ctypes.c_int
-    assert lib.spectre_mix_abi_version() == 1
+    assert lib.spectre_mix_abi_version() == 2
     lib.spectre_mix_last_error.restype = ctypes.c_char_p
     assert isinstance(lib.spectre_mix_last_error(), bytes)
 

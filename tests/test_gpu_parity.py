@@ -279,6 +279,123 @@ def test_host_entry_point(fb, oracle):
     _check(got2, oracle.mix_flat(V, gate, 1024, 16).numpy())
 
 
+@pytest.mark.parametrize("n_fft,B,C,dg", [(8192, 5, 64, 16), (16384, 4, 64, 16), (8192, 4, 768, 16), (16384, 4, 768, 16)])
+def test_host_entry_point_long_context(n_fft, B, C, dg, fb, oracle):
+    """spectre_mix_fwd_host at n_fft = 8192 / 16384 with several chunks in flight (one batch row per chunk at C = 768: the
+    chunks run on 4 streams, each with its OWN workspace -- the round-1 per-device scratch raced here)."""
+    V, gate, mem = _rand_case(B, n_fft - 100, n_fft, C, dg, C == 64, seed=140 + B + C)
+    want = oracle.mix_flat(V, gate, n_fft, dg, mem).numpy()
+    import os
+    old = os.environ.get("SPECTRE_MIX_HOST_CHUNK_MB")
+    if C == 64:
+        os.environ["SPECTRE_MIX_HOST_CHUNK_MB"] = "4"       # force one row per chunk at the narrow shape too
+    try:
+        got = fb.spectral_mix_host(V, gate, mem, n_fft=n_fft, group_width=dg)
+    finally:
+        if old is None:
+            os.environ.pop("SPECTRE_MIX_HOST_CHUNK_MB", None)
+        else:
+            os.environ["SPECTRE_MIX_HOST_CHUNK_MB"] = old
+    _check(got, want)
+    with pytest.raises(ValueError):
+        fb.spectral_mix_host(V, gate, mem, n_fft=n_fft, group_width=dg, out=torch.empty(B, 8, C))
+
+
+def test_long_context_concurrent_streams_and_workspace(fb, oracle, dev):
+    """Two side streams run the n_fft = 16384 path at the same time (different inputs): results are bit-equal to the serial
+    ones, through the torch op (workspace from the caching allocator), through the plain C entry without a workspace
+    (stream-ordered pool allocation per call) and through spectre_mix_fwd_ws with caller-owned scratch."""
+    import ctypes
+    from fft_b200 import _lib
+    lib = _lib.load()
+    n_fft, C, dg, B = 16384, 256, 16, 6
+    ins = []
+    for i in range(2):
+        V, gate, _ = _rand_case(B, n_fft, n_fft, C, dg, False, seed=170 + i)
+        ins.append((V.to(dev), gate.to(dev)))
+    serial = [fb.spectral_mix(V, g, n_fft=n_fft, group_width=dg).clone() for V, g in ins]
+    _check(serial[0][:1], oracle.mix_flat(ins[0][0][:1].cpu(), ins[0][1][:1].cpu(), n_fft, dg).numpy())
+    need = lib.spectre_mix_workspace_bytes(0, B, n_fft, n_fft, C, dg)
+    assert need == B * n_fft * C * 4 and fb.plan_info(B, n_fft, n_fft, C, dg)["workspace_bytes"] == need
+    assert lib.spectre_mix_workspace_bytes(0, B, 4096, 4096, C, dg) == 0
+
+    def call(kind, V, g, out, ws, stream):
+        args = (V.data_ptr(), 0, V.stride(0), V.stride(1), g.data_ptr(), None, 0, out.data_ptr(), 0, out.stride(0), out.stride(1),
+                B, n_fft, n_fft, C, dg)
+        if kind == "plain":
+            rc = lib.spectre_mix_fwd(*args, ctypes.c_void_p(stream.cuda_stream))
+        else:
+            rc = lib.spectre_mix_fwd_ws(*args, ws.data_ptr(), ws.numel(), ctypes.c_void_p(stream.cuda_stream))
+        _lib.check(rc, kind)
+
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    for kind in ("op", "plain", "ws"):
+        for rep in range(3):
+            outs = [torch.empty_like(serial[0]) for _ in range(2)]
+            wss = [torch.empty(need, dtype=torch.uint8, device=dev) for _ in range(2)]
+            torch.cuda.synchronize()
+            for i, st in enumerate(streams):
+                with torch.cuda.stream(st):
+                    for _ in range(2):      # back to back on each stream as well
+                        if kind == "op":
+                            outs[i] = fb.spectral_mix(*ins[i], n_fft=n_fft, group_width=dg)
+                        else:
+                            call(kind, ins[i][0], ins[i][1], outs[i], wss[i], st)
+            torch.cuda.synchronize()
+            for i in range(2):
+                assert torch.equal(outs[i], serial[i]), (kind, rep, i)
+    # a workspace that is too small is refused, not overrun
+    small = torch.empty(need // 2, dtype=torch.uint8, device=dev)
+    rc = lib.spectre_mix_fwd_ws(ins[0][0].data_ptr(), 0, ins[0][0].stride(0), ins[0][0].stride(1), ins[0][1].data_ptr(), None, 0,
+                                outs[0].data_ptr(), 0, outs[0].stride(0), outs[0].stride(1), B, n_fft, n_fft, C, dg,
+                                small.data_ptr(), small.numel(), None)
+    assert rc == 1 and b"workspace too small" in lib.spectre_mix_last_error()
+
+
+def test_cuda_graph_capture_long_context(fb, dev):
+    """n_fft = 16384 (three launches around a workspace) captured into a CUDA graph and replayed on new data: through the
+    torch op and through the plain C entry (stream-ordered allocation inside the capture)."""
+    import ctypes
+    from fft_b200 import _lib
+    lib = _lib.load()
+    n_fft, C, dg, B = 16384, 64, 16, 3
+    V, gate, _ = _rand_case(B, n_fft, n_fft, C, dg, False, seed=178)
+    Vd, gd = V.to(dev), gate.to(dev)
+    ref1 = fb.spectral_mix(Vd, gd, n_fft=n_fft, group_width=dg).clone()          # warm-up (twiddle tables)
+    ref2 = fb.spectral_mix(2.0 * Vd, gd, n_fft=n_fft, group_width=dg).clone()
+    static_in = Vd.clone()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        static_out = fb.spectral_mix(static_in, gd, n_fft=n_fft, group_width=dg)
+    graph.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(static_out, ref1)
+    static_in.copy_(2.0 * Vd)
+    graph.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(static_out, ref2)
+    out2 = torch.empty_like(ref1)
+    g2 = torch.cuda.CUDAGraph()
+    static_in.copy_(Vd)
+    # one warm-up call of the plain entry outside the capture (creates the device's private pool)
+    _lib.check(lib.spectre_mix_fwd(static_in.data_ptr(), 0, static_in.stride(0), static_in.stride(1), gd.data_ptr(), None, 0,
+                                   out2.data_ptr(), 0, out2.stride(0), out2.stride(1), B, n_fft, n_fft, C, dg,
+                                   ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)), "warm-up")
+    torch.cuda.synchronize()
+    with torch.cuda.graph(g2):
+        rc = lib.spectre_mix_fwd(static_in.data_ptr(), 0, static_in.stride(0), static_in.stride(1), gd.data_ptr(), None, 0,
+                                 out2.data_ptr(), 0, out2.stride(0), out2.stride(1), B, n_fft, n_fft, C, dg,
+                                 ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+        _lib.check(rc, "spectre_mix_fwd under capture")
+    g2.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(out2, ref1)
+    static_in.copy_(2.0 * Vd)
+    g2.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(out2, ref2)
+
+
 def test_plan_info(fb):
     info = fb.plan_info(8, 4096, 4096, 768, 16)
     assert info["n_fft"] == 4096 and np.prod(info["radix"]) == 4096
@@ -420,10 +537,32 @@ def test_decode_split_equals_fused(fb, dev):
         gate = torch.randn(d // dg, n // 2 + 1, dtype=torch.cfloat, device=dev)
         c1.decode_step(q, v)
         a = c1.readout(gate, c1.t % n)
-        v_old, _ = c2._advance(q, v)
-        b = c2.fused_step(v, v_old, gate)
+        j = c2._advance(q)
+        b = c2.fused_step(v, c2.V_buf[j], gate)
+        c2._store_v(j, v)
         assert torch.allclose(a, b, rtol=1e-5, atol=1e-5)
     assert torch.equal(c1.prefix_fft, c2.prefix_fft)
+
+
+def test_decode_gate_kernel_matches_stock_ops_and_is_deterministic(fb, dev):
+    """spectre_decode_gate (interp + modReLU + decode phase in one launch) against the stock PyTorch op sequence of
+    spectre.py:578-598, before and after the window is full (phase angle in the reference's float32 rounding order);
+    the read-out is bit-reproducible run to run (two-stage fixed-order reduction, no atomics)."""
+    from fft_b200.decode import decode_gate, decode_gate_torch
+    torch.manual_seed(31)
+    n, d = 256, 32
+    head = fb.SpectreHead(d, n, pooling_type="mean").to(dev).eval()
+    cache = fb.PrefixFFTCache(n, d, device=dev)
+    cache.prefill(torch.randn(200, d, device=dev), torch.randn(200, d, device=dev))
+    for t in (210, 255, 256, 300, 1000, 5000):
+        cache.t = t
+        a, b = decode_gate(head, cache), decode_gate_torch(head, cache)
+        assert a.shape == b.shape == (head.G, head.F_half)
+        assert rel_l2(torch.view_as_real(a).cpu().numpy(), torch.view_as_real(b).cpu().numpy()) < 2e-5, t
+    cache.t = 230
+    gate = torch.randn(d // 8, n // 2 + 1, dtype=torch.cfloat, device=dev)
+    outs = [cache.readout(gate, 17).clone() for _ in range(5)]
+    assert all(torch.equal(outs[0], o) for o in outs[1:])
 
 
 # --------------------------------------------------------------------------- BASELINE config 3: full model, bf16
