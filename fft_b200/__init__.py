@@ -10,7 +10,7 @@ MLP) stays stock PyTorch, exactly as in the reference.
 There is no CPU path in this package: importing it works anywhere, but calling the op
 without the CUDA library or a GPU raises.
 """
-from .ops import gate_expand, rfft_seq, spectral_mix, spectral_mix_host, plan_info  # noqa: F401
+from .ops import gate_expand, rfft_seq, spectral_mix, spectral_mix_anchors, spectral_mix_host, plan_info  # noqa: F401
 from .decode import PrefixFFTCache, decode_gate, head_decode_step  # noqa: F401
 from .model import SpectreBase  # noqa: F401
 from .modules import (  # noqa: F401
@@ -24,7 +24,7 @@ from .modules import (  # noqa: F401
 )
 
 __all__ = [
-    "spectral_mix", "spectral_mix_host", "rfft_seq", "gate_expand", "plan_info",
+    "spectral_mix", "spectral_mix_anchors", "spectral_mix_host", "rfft_seq", "gate_expand", "plan_info",
     "SpectreHead", "SpectreMultiHead", "SpectreBlock", "WaveletRefinement", "ComplexModReLU",
     "interp_complex_1d", "patch_reference", "PrefixFFTCache", "head_decode_step", "decode_gate", "SpectreBase",
 ]

@@ -21,6 +21,8 @@ SYMBOLS = (
     "spectre_mix_last_error",
     "spectre_mix_fwd",
     "spectre_mix_fwd_ws",
+    "spectre_mix_fwd_anchors",
+    "spectre_mix_anchors_workspace_bytes",
     "spectre_mix_workspace_bytes",
     "spectre_mix_fwd_host",
     "spectre_rfft_fwd",
@@ -89,6 +91,11 @@ def load():
                                            ctypes.c_size_t, vp]
         lib.spectre_mix_workspace_bytes.restype = ctypes.c_size_t
         lib.spectre_mix_workspace_bytes.argtypes = [i32, i32, i32, i32, i32, i32]
+        lib.spectre_mix_fwd_anchors.restype = i32
+        lib.spectre_mix_fwd_anchors.argtypes = [vp, i32, i64, i64, vp, vp, vp, vp, i64, i32, i32, vp, i64, vp, i32, i64, i64,
+                                                i32, i32, i32, i32, i32, vp, ctypes.c_size_t, vp]
+        lib.spectre_mix_anchors_workspace_bytes.restype = ctypes.c_size_t
+        lib.spectre_mix_anchors_workspace_bytes.argtypes = [i32, i32, i32, i32, i32, i32]
         lib.spectre_mix_fwd_host.restype = i32
         lib.spectre_mix_fwd_host.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32]
         lib.spectre_rfft_fwd.restype = i32

@@ -7,6 +7,9 @@
 #include <stdint.h>
 
 #include <algorithm>
+#include <map>
+#include <mutex>
+#include <tuple>
 
 #include "../../include/spectre_mix.h"
 #include "spectre_gate.cuh"
@@ -50,7 +53,51 @@ int check_args(const void *anchors, const float *bias, const float *eps, void *g
 
 int grid_for(long long total) { return (int)std::min<long long>((total + 255) / 256, 1 << 20); }
 
+__global__ void gate_interp_table_kernel(int F_half, int Bk, float4 *coef, ushort4 *tap) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= F_half) return;
+    float4 c;
+    int tp[4];
+    spx::gate_interp_of(k, F_half, Bk, c, tp);
+    coef[k] = c;
+    tap[k] = make_ushort4((unsigned short)tp[0], (unsigned short)tp[1], (unsigned short)tp[2], (unsigned short)tp[3]);
+}
+
+struct InterpTable {
+    float4 *coef = nullptr;
+    ushort4 *tap = nullptr;
+};
+std::mutex g_tab_mu;
+std::map<std::tuple<int, int, int>, InterpTable> g_tabs;   // (device, F_half, Bk)
+
 }  // namespace
+
+namespace spx {
+int gate_interp_table(int F_half, int Bk, const float4 **icoef, const ushort4 **itap) {
+    *icoef = nullptr;
+    *itap = nullptr;
+    if (Bk > 65535) return 0;   // taps do not fit 16 bits: the kernel derives them per bin instead
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaGetDevice");
+    std::lock_guard<std::mutex> lock(g_tab_mu);
+    auto key = std::make_tuple(dev, F_half, Bk);
+    auto it = g_tabs.find(key);
+    if (it == g_tabs.end()) {
+        InterpTable t;
+        if ((e = cudaMalloc(&t.coef, sizeof(float4) * (size_t)F_half)) != cudaSuccess) return cuda_fail(e, "cudaMalloc(interp table)");
+        if ((e = cudaMalloc(&t.tap, sizeof(ushort4) * (size_t)F_half)) != cudaSuccess) { cudaFree(t.coef); return cuda_fail(e, "cudaMalloc(interp table)"); }
+        gate_interp_table_kernel<<<(F_half + 255) / 256, 256>>>(F_half, Bk, t.coef, t.tap);
+        e = cudaGetLastError();
+        if (e == cudaSuccess) e = cudaDeviceSynchronize();   // first use only: the table is complete before anyone reads it
+        if (e != cudaSuccess) { cudaFree(t.coef); cudaFree(t.tap); return cuda_fail(e, "interpolation table kernel"); }
+        it = g_tabs.emplace(key, t).first;
+    }
+    *icoef = it->second.coef;
+    *itap = it->second.tap;
+    return 0;
+}
+}  // namespace spx
 
 extern "C" int spectre_gate_expand(const void *anchors, const float *bias, const float *eps, const void *pos_phase,
                                    long long pos_stride_b, void *gate, int B, int NG, int G, int Bk, int F_half, void *stream) {

@@ -27,6 +27,11 @@ struct GateSrc {
     long long pos_stride_b;  // 0 = one phase row shared by the batch
     int Bk;                  // anchors per gate row
     int G;                   // gate rows per head (the scope of the reference's real/imag row shuffle)
+    // Optional per-(F_half, Bk) interpolation table (built once per device by the library, spectre_gate.cu): the four cubic
+    // coefficients and the four clamped tap indices of every bin depend on k only, so the mix kernel's gate staging reads
+    // them (24 B per bin, L2-resident) instead of re-deriving them for every (batch row, gate row).  nullptr = compute.
+    const float4 *icoef;     // [F_half] (c0, c1, c2, c3)
+    const ushort4 *itap;     // [F_half] (t0, t1, t2, t3)
 };
 
 __device__ __forceinline__ float cubic_conv1(float x, float A) { return ((A + 2.f) * x - (A + 3.f)) * x * x + 1.f; }
@@ -38,10 +43,8 @@ __device__ __forceinline__ float plane_tap(const float2 *__restrict__ a, int Bk,
     return __ldg(p + r / G);
 }
 
-// gate value of bin k (< F_half) of gate row j (< G) of one (sample, head); `a` = that head's [G][Bk] anchors; bias / eps /
-// pos already offset to the row
-__device__ __forceinline__ float2 gate_from_anchors(const float2 *__restrict__ a, int Bk, int G, int j, int k, int F_half,
-                                                    float bias, float eps, const float2 *__restrict__ pos) {
+// cubic-convolution coefficients and clamped taps of bin k: ATen's grid sampler on torch.linspace(-1, 1, F_half)
+__device__ __forceinline__ void gate_interp_of(int k, int F_half, int Bk, float4 &c, int (&tp)[4]) {
     // torch.linspace(-1, 1, F_half): symmetric evaluation around the middle
     const float step = 2.f / (float)(F_half - 1);
     const float gx = (k < F_half / 2) ? -1.f + step * (float)k : 1.f - step * (float)(F_half - 1 - k);
@@ -50,17 +53,61 @@ __device__ __forceinline__ float2 gate_from_anchors(const float2 *__restrict__ a
     const float t = ix - fl;
     const int i1 = (int)fl;
     constexpr float A = -0.75f;
-    const float c0 = cubic_conv2(t + 1.f, A), c1 = cubic_conv1(t, A), c2 = cubic_conv1(1.f - t, A), c3 = cubic_conv2(2.f - t, A);
+    c = make_float4(cubic_conv2(t + 1.f, A), cubic_conv1(t, A), cubic_conv1(1.f - t, A), cubic_conv2(2.f - t, A));
     const int hi = Bk - 1;
-    const int t0 = min(max(i1 - 1, 0), hi), t1 = min(max(i1, 0), hi), t2 = min(max(i1 + 1, 0), hi), t3 = min(max(i1 + 2, 0), hi);
+    tp[0] = min(max(i1 - 1, 0), hi); tp[1] = min(max(i1, 0), hi); tp[2] = min(max(i1 + 1, 0), hi); tp[3] = min(max(i1 + 2, 0), hi);
+}
+
+// interpolated anchors of gate row j at bin k (before modReLU); coefficients in the grid sampler's summation order
+__device__ __forceinline__ float2 gate_interp_eval(const float2 *__restrict__ a, int Bk, int G, int j, const float4 &c, const int (&tp)[4]) {
     const int r0 = 2 * j, r1 = 2 * j + 1;
     float2 z;
-    z.x = plane_tap(a, Bk, G, r0, t0) * c0 + plane_tap(a, Bk, G, r0, t1) * c1 + plane_tap(a, Bk, G, r0, t2) * c2 +
-          plane_tap(a, Bk, G, r0, t3) * c3;
-    z.y = plane_tap(a, Bk, G, r1, t0) * c0 + plane_tap(a, Bk, G, r1, t1) * c1 + plane_tap(a, Bk, G, r1, t2) * c2 +
-          plane_tap(a, Bk, G, r1, t3) * c3;
+    z.x = plane_tap(a, Bk, G, r0, tp[0]) * c.x + plane_tap(a, Bk, G, r0, tp[1]) * c.y + plane_tap(a, Bk, G, r0, tp[2]) * c.z +
+          plane_tap(a, Bk, G, r0, tp[3]) * c.w;
+    z.y = plane_tap(a, Bk, G, r1, tp[0]) * c.x + plane_tap(a, Bk, G, r1, tp[1]) * c.y + plane_tap(a, Bk, G, r1, tp[2]) * c.z +
+          plane_tap(a, Bk, G, r1, tp[3]) * c.w;
+    return z;
+}
+
+// gate value of bin k (< F_half) of gate row j (< G) of one (sample, head); `a` = that head's [G][Bk] anchors; bias / eps /
+// pos already offset to the row.  The stand-alone expansion kernel: IEEE square root and division as ATen evaluates them.
+__device__ __forceinline__ float2 gate_from_anchors(const float2 *__restrict__ a, int Bk, int G, int j, int k, int F_half,
+                                                    float bias, float eps, const float2 *__restrict__ pos) {
+    float4 c;
+    int tp[4];
+    gate_interp_of(k, F_half, Bk, c, tp);
+    float2 z = gate_interp_eval(a, Bk, G, j, c, tp);
     const float mag = sqrtf(z.x * z.x + z.y * z.y);
     const float scale = fmaxf(mag + bias, 0.f) / sqrtf(mag * mag + eps * eps);
+    z.x *= scale;
+    z.y *= scale;
+    if (pos) {
+        const float2 p = __ldg(pos + k);
+        z = make_float2(z.x * p.x - z.y * p.y, z.x * p.y + z.y * p.x);
+    }
+    return z;
+}
+
+// The same function for the mix kernel's gate staging, where it runs once per (tile, bin) on the kernel's critical path: the
+// k-only part comes from the table when the library built one, and modReLU uses the reciprocal square root unit
+// (|z| = m2 * rsqrt(m2), scale = relu(|z| + b) * rsqrt(m2 + eps^2); MUFU.RSQ is accurate to 2 ulp -- well inside the 1e-5 bar,
+// checked against the reference-generated gate goldens through the fused entry).
+__device__ __forceinline__ float2 gate_from_anchors_fast(const float4 *__restrict__ icoef, const ushort4 *__restrict__ itap, int Bk, int G,
+                                                         const float2 *__restrict__ a, int j, int k, int F_half, float bias, float eps,
+                                                         const float2 *__restrict__ pos) {
+    float4 c;
+    int tp[4];
+    if (icoef) {
+        c = __ldg(icoef + k);
+        const ushort4 t = __ldg(itap + k);
+        tp[0] = t.x; tp[1] = t.y; tp[2] = t.z; tp[3] = t.w;
+    } else {
+        gate_interp_of(k, F_half, Bk, c, tp);
+    }
+    float2 z = gate_interp_eval(a, Bk, G, j, c, tp);
+    const float m2 = z.x * z.x + z.y * z.y;
+    const float mag = m2 * rsqrtf(fmaxf(m2, 1e-37f));
+    const float scale = fmaxf(mag + bias, 0.f) * rsqrtf(fmaf(eps, eps, m2));
     z.x *= scale;
     z.y *= scale;
     if (pos) {

@@ -351,8 +351,8 @@ const KernelEntry *find_sub_kernel() {
 // pre pass (radix-R stage + twiddles) -> 4096-point shared-memory kernel on R interleaved sub-transforms (in place in
 // the scratch tensor) -> post pass.  Three launches, each streaming the tensor once.
 int mix_two_pass_rows(DeviceState &st, const KernelEntry &k, const void *v, int dtype, long long v_sb, long long v_sn, const void *gate,
-                      const void *mem, long long mem_stride, void *out, long long o_sb, long long o_sn, int B, int n_io, int n_fft,
-                      int C, int group_width, float *scr, cudaStream_t stream) {
+                      const spx::GateSrc *gs, const void *mem, long long mem_stride, void *out, long long o_sb, long long o_sn, int B,
+                      int n_io, int n_fft, int C, int group_width, float *scr, cudaStream_t stream) {
     const int sub = 4096, R = n_fft / sub;
     cudaError_t e = spx::long_pass(true, R, dtype == SPECTRE_MIX_BF16, v, scr, v_sb, v_sn, B, n_io, C, sub, st.sm_count, stream);
     if (e != cudaSuccess) return cuda_fail(e, "long-context pre pass");
@@ -364,6 +364,7 @@ int mix_two_pass_rows(DeviceState &st, const KernelEntry &k, const void *v, int 
     p.v = scr;
     p.out = scr;
     p.gate = reinterpret_cast<const float2 *>(gate);
+    if (gs) p.gsrc = *gs;                    // gate == nullptr: the sub-transform kernel evaluates the gate from the anchors
     p.mem = reinterpret_cast<const float2 *>(mem);
     p.tw = tw;
     p.v_sb = p.o_sb = (long long)sub * C;
@@ -399,7 +400,8 @@ int mix_two_pass_rows(DeviceState &st, const KernelEntry &k, const void *v, int 
     if (!tma && (int)k.smem_bytes(2, false, false) > st.max_smem_optin)
         return fail(SPECTRE_MIX_ERR_UNSUPPORTED, "internal: sub-transform kernel does not fit shared memory");
     const int occ = std::max(1, occupancy_of(st, c, mem != nullptr, tma, tmem));
-    const int grid = std::min(p.num_tiles, st.sm_count * occ);
+    p.pair_tiles = (tmem && (p.sched & 16) && p.tiles_per_row % 2 == 0 && group_width % (2 * tile_ch) == 0) ? 1 : 0;
+    const int grid = std::min(p.pair_tiles ? p.num_tiles / 2 : p.num_tiles, st.sm_count * occ);
     e = k.launch(p, grid, mem != nullptr, tma ? &tmap : nullptr, tma ? &tmap_out : nullptr, tmem, stream);
     if (e != cudaSuccess) return cuda_fail(e, "long-context sub-transform kernel");
 
@@ -423,45 +425,29 @@ const KernelEntry *two_pass_kernel(int n_fft, int mode, int group_width, const v
     return find_sub_kernel();
 }
 
-// The complex intermediate [rows][R][4096][C] fp32 lives in `ws` -- the caller's workspace when one was passed
-// (spectre_mix_fwd_ws), else a stream-ordered allocation from the device's private pool made on THIS call's stream, so two
-// calls on different streams never share a buffer (the round-1 per-device scratch did, and raced).  With the chunk knob the
-// batch is walked in chunks of rows whose intermediate is small enough to stay in the 126 MB L2 between the three launches.
-int mix_two_pass(DeviceState &st, int dev, const KernelEntry &k, const void *v, int dtype, long long v_sb, long long v_sn,
-                 const void *gate, const void *mem, long long mem_stride, void *out, long long o_sb, long long o_sn, int B, int n_io,
-                 int n_fft, int C, int group_width, void *ws, size_t ws_bytes, cudaStream_t stream) {
-    const size_t row_bytes = (size_t)n_fft * C * sizeof(float);
+// The complex intermediate [rows][R][4096][C] fp32 lives in `scr` (the caller's workspace or a stream-ordered allocation made
+// for this call, see mix_fwd_impl).  With the chunk knob the batch is walked in chunks of rows whose intermediate is small
+// enough to stay in the 126 MB L2 between the three launches.
+int mix_two_pass(DeviceState &st, const KernelEntry &k, const void *v, int dtype, long long v_sb, long long v_sn,
+                 const void *gate, const spx::GateSrc *gs, const void *mem, long long mem_stride, void *out, long long o_sb,
+                 long long o_sn, int B, int n_io, int n_fft, int C, int group_width, float *scr, cudaStream_t stream) {
     const int rows = two_pass_rows(B, n_fft, C);
-    const size_t need = (size_t)rows * row_bytes;
-    float *scr = nullptr;
-    bool pooled = false;
-    if (ws) {
-        if (ws_bytes < need)
-            return fail(SPECTRE_MIX_ERR_BAD_ARG, "workspace too small: %zu bytes given, spectre_mix_workspace_bytes() = %zu", ws_bytes, need);
-        if (!aligned(ws, 16)) return fail(SPECTRE_MIX_ERR_UNSUPPORTED, "workspace must be 16-byte aligned");
-        scr = reinterpret_cast<float *>(ws);
-    } else {
-        cudaMemPool_t pool = nullptr;
-        if (int rc = get_pool(st, dev, &pool)) return rc;
-        void *pm = nullptr;
-        cudaError_t e = cudaMallocFromPoolAsync(&pm, need, pool, stream);
-        if (e != cudaSuccess) return cuda_fail(e, "cudaMallocFromPoolAsync(long-context scratch)");
-        scr = reinterpret_cast<float *>(pm);
-        pooled = true;
-    }
     const size_t es = dtype == SPECTRE_MIX_F32 ? 4 : 2;
-    const size_t gate_row = (size_t)(C / group_width) * (n_fft / 2 + 1) * sizeof(float2);
+    const int NG = C / group_width;
+    const size_t gate_row = (size_t)NG * (n_fft / 2 + 1) * sizeof(float2);
     int rc = 0;
     for (int b0 = 0; b0 < B && !rc; b0 += rows) {
         const int nb = std::min(rows, B - b0);
+        spx::GateSrc gsub;
+        if (gs) {   // anchors / phase of this chunk of batch rows
+            gsub = *gs;
+            gsub.anchors += (size_t)b0 * NG * gs->Bk;
+            if (gsub.pos) gsub.pos += (size_t)b0 * gs->pos_stride_b;
+        }
         rc = mix_two_pass_rows(st, k, reinterpret_cast<const char *>(v) + (size_t)b0 * v_sb * es, dtype, v_sb, v_sn,
-                               reinterpret_cast<const char *>(gate) + (size_t)b0 * gate_row, mem, mem_stride,
-                               reinterpret_cast<char *>(out) + (size_t)b0 * o_sb * es, o_sb, o_sn, nb, n_io, n_fft, C, group_width,
-                               scr, stream);
-    }
-    if (pooled) {
-        cudaError_t e = cudaFreeAsync(scr, stream);   // stream-ordered: the memory goes back to the pool after the post pass
-        if (e != cudaSuccess && !rc) rc = cuda_fail(e, "cudaFreeAsync(long-context scratch)");
+                               gate ? reinterpret_cast<const char *>(gate) + (size_t)b0 * gate_row : nullptr, gs ? &gsub : nullptr,
+                               mem, mem_stride, reinterpret_cast<char *>(out) + (size_t)b0 * o_sb * es, o_sb, o_sn, nb, n_io, n_fft,
+                               C, group_width, scr, stream);
     }
     return rc;
 }
@@ -521,19 +507,30 @@ int spectre_mix_set_tma(int enable) {
 }
 
 namespace {
-int mix_fwd_impl(const void *v, int v_dtype, int64_t v_stride_b, int64_t v_stride_n, const void *gate, const void *mem,
-                 int64_t mem_stride, void *out, int out_dtype, int64_t out_stride_b, int64_t out_stride_n, int B, int N, int n_fft,
-                 int C, int group_width, void *ws, size_t ws_bytes, void *stream) {
+size_t align256(size_t x) { return (x + 255) / 256 * 256; }
+
+// `gs` != nullptr: the gate comes from anchors (spectre_mix_fwd_anchors) and `gate` is null
+int mix_fwd_impl(const void *v, int v_dtype, int64_t v_stride_b, int64_t v_stride_n, const void *gate, const spx::GateSrc *gs,
+                 const void *mem, int64_t mem_stride, void *out, int out_dtype, int64_t out_stride_b, int64_t out_stride_n, int B,
+                 int N, int n_fft, int C, int group_width, void *ws, size_t ws_bytes, void *stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
     if (int rc = check_common(B, N, n_fft, C, group_width)) return rc;
     if (v_dtype != out_dtype || (v_dtype != SPECTRE_MIX_F32 && v_dtype != SPECTRE_MIX_BF16))
         return fail(SPECTRE_MIX_ERR_UNSUPPORTED, "dtype pair (%d, %d) unsupported: V and out must both be f32 or both bf16",
                     v_dtype, out_dtype);
     const int n_io = std::min(N, n_fft);
     if (B == 0 || C == 0 || n_io == 0) return 0;  // empty input: nothing to write
-    if (!v || !gate || !out) return fail(SPECTRE_MIX_ERR_BAD_ARG, "null pointer (v=%p gate=%p out=%p)", v, gate, out);
-    if (!aligned(gate, 8)) return fail(SPECTRE_MIX_ERR_UNSUPPORTED, "gate must be 8-byte aligned");
+    if (!v || (!gate && !gs) || !out) return fail(SPECTRE_MIX_ERR_BAD_ARG, "null pointer (v=%p gate=%p out=%p)", v, gate, out);
+    if (gate && !aligned(gate, 8)) return fail(SPECTRE_MIX_ERR_UNSUPPORTED, "gate must be 8-byte aligned");
     if (mem && !aligned(mem, 8)) return fail(SPECTRE_MIX_ERR_UNSUPPORTED, "memory must be 8-byte aligned");
     if (mem && mem_stride < C) return fail(SPECTRE_MIX_ERR_BAD_ARG, "mem_stride=%lld < C=%d", (long long)mem_stride, C);
+    const int NG = C / group_width, F_half = n_fft / 2 + 1;
+    if (gs) {
+        if (!gs->anchors || !gs->bias || !gs->eps) return fail(SPECTRE_MIX_ERR_BAD_ARG, "null pointer (anchors / bias / eps)");
+        if (gs->G <= 0 || NG % gs->G != 0 || gs->Bk < 1)
+            return fail(SPECTRE_MIX_ERR_BAD_ARG, "anchors: NG=%d is not a multiple of G=%d, or Bk=%d < 1", NG, gs->G, gs->Bk);
+        if (!aligned(gs->anchors, 8) || (gs->pos && !aligned(gs->pos, 8))) return fail(SPECTRE_MIX_ERR_UNSUPPORTED, "anchors / phase must be 8-byte aligned");
+    }
 
     DeviceState *st = nullptr;
     int dev = 0;
@@ -541,19 +538,64 @@ int mix_fwd_impl(const void *v, int v_dtype, int64_t v_stride_b, int64_t v_strid
 
     const int mode = pick_mode(v_dtype, group_width, v, v_stride_b, v_stride_n, out, out_stride_b, out_stride_n, mem,
                                mem_stride);
-    // long transforms: one streaming radix-R pass, R interleaved 4096-point transforms in shared memory, one streaming pass
-    if (const KernelEntry *ks = two_pass_kernel(n_fft, mode, group_width, mem, mem_stride))
-        return mix_two_pass(*st, dev, *ks, v, v_dtype, v_stride_b, v_stride_n, gate, mem, mem_stride, out, out_stride_b,
-                            out_stride_n, B, n_io, n_fft, C, group_width, ws, ws_bytes, reinterpret_cast<cudaStream_t>(stream));
+    const KernelEntry *ks = two_pass_kernel(n_fft, mode, group_width, mem, mem_stride);
     Choice c;
-    if (int rc = choose(*st, n_fft, v_dtype, mode, C, group_width, &c)) return rc;
+    if (!ks) {
+        if (int rc = choose(*st, n_fft, v_dtype, mode, C, group_width, &c)) return rc;
+    }
+    // scratch of this call: [long-context intermediate][materialised gate, when this layout has no in-kernel gate generator]
+    const bool fused_gate = gs && (ks ? ks->anch_ok : c.k->anch_ok);
+    const size_t need_long = ks ? (size_t)two_pass_rows(B, n_fft, C) * (size_t)n_fft * C * sizeof(float) : 0;
+    const size_t need_gate = (gs && !fused_gate) ? (size_t)B * NG * F_half * sizeof(float2) : 0;
+    const size_t need = align256(need_long) + need_gate;
+    char *scr = nullptr;
+    bool pooled = false;
+    if (need) {
+        if (ws) {
+            if (ws_bytes < need)
+                return fail(SPECTRE_MIX_ERR_BAD_ARG, "workspace too small: %zu bytes given, %zu needed (spectre_mix%s_workspace_bytes)",
+                            ws_bytes, need, gs ? "_anchors" : "");
+            if (!aligned(ws, 16)) return fail(SPECTRE_MIX_ERR_UNSUPPORTED, "workspace must be 16-byte aligned");
+            scr = reinterpret_cast<char *>(ws);
+        } else {
+            // no workspace passed: a stream-ordered allocation from the device's private pool on THIS call's stream -- two calls
+            // on different streams never share a buffer (the round-1 per-device scratch did, and raced), nothing synchronises
+            // the device, and the pair alloc / free is legal under stream capture
+            cudaMemPool_t pool = nullptr;
+            if (int rc = get_pool(*st, dev, &pool)) return rc;
+            void *pm = nullptr;
+            cudaError_t e = cudaMallocFromPoolAsync(&pm, need, pool, stream);
+            if (e != cudaSuccess) return cuda_fail(e, "cudaMallocFromPoolAsync(scratch)");
+            scr = reinterpret_cast<char *>(pm);
+            pooled = true;
+        }
+    }
+    auto finish = [&](int rc) {
+        if (pooled) {
+            cudaError_t e = cudaFreeAsync(scr, stream);   // stream-ordered: back to the pool after the last launch of this call
+            if (e != cudaSuccess && !rc) rc = cuda_fail(e, "cudaFreeAsync(scratch)");
+        }
+        return rc;
+    };
+    if (need_gate) {   // layouts without a fused variant (odd group widths, misaligned rows): expand, then the plain kernels
+        void *gbuf = scr + align256(need_long);
+        if (int rc = spectre_gate_expand(gs->anchors, gs->bias, gs->eps, gs->pos, gs->pos_stride_b, gbuf, B, NG, gs->G, gs->Bk, F_half, stream_))
+            return finish(rc);
+        gate = gbuf;
+        gs = nullptr;
+    }
+    // long transforms: one streaming radix-R pass, R interleaved 4096-point transforms in shared memory, one streaming pass
+    if (ks)
+        return finish(mix_two_pass(*st, *ks, v, v_dtype, v_stride_b, v_stride_n, gate, gs, mem, mem_stride, out, out_stride_b,
+                                   out_stride_n, B, n_io, n_fft, C, group_width, reinterpret_cast<float *>(scr), stream));
     const float2 *tw = nullptr;
-    if (int rc = get_twiddles(*st, *c.k, &tw)) return rc;
+    if (int rc = get_twiddles(*st, *c.k, &tw)) return finish(rc);
 
     MixParams p;
     memset(&p, 0, sizeof(p));
     p.v = v;
     p.gate = reinterpret_cast<const float2 *>(gate);
+    if (gs) p.gsrc = *gs;
     p.mem = reinterpret_cast<const float2 *>(mem);
     p.out = out;
     p.tw = tw;
@@ -567,7 +609,7 @@ int mix_fwd_impl(const void *v, int v_dtype, int64_t v_stride_b, int64_t v_strid
     p.n_out = n_io;
     p.C = C;
     p.group_width = group_width;
-    p.NG = C / group_width;
+    p.NG = NG;
     p.tiles_per_row = c.tiles_per_row;
     p.num_tiles = B * c.tiles_per_row;
     p.gate_tables = c.gate_tables;
@@ -591,19 +633,20 @@ int mix_fwd_impl(const void *v, int v_dtype, int64_t v_stride_b, int64_t v_strid
                make_v_tensor_map(&tmap_out, out, out_dtype, out_stride_b, out_stride_n, B, n_io, C, c.k->out_box_rows, tile_ch);
     const bool tmem = tma && use_tmem && c.k->tmem_ok && (int)c.k->smem_bytes(c.gate_tables, true, true) <= st->max_smem_optin;
     const int occ = std::max(1, occupancy_of(*st, c, mem != nullptr, tma, tmem));
-    const int grid = std::min(p.num_tiles, st->sm_count * occ);
-    cudaError_t e = c.k->launch(p, grid, mem != nullptr, tma ? &tmap : nullptr, tma ? &tmap_out : nullptr, tmem,
-                                reinterpret_cast<cudaStream_t>(stream));
-    if (e != cudaSuccess) return cuda_fail(e, "kernel launch");
-    return 0;
+    // paired tile order (TMEM variant): the two channel tiles of one gate group back to back, gate row staged once for both
+    p.pair_tiles = (tmem && (p.sched & 16) && c.gate_tables == 1 && c.tiles_per_row % 2 == 0 && group_width % (2 * tile_ch) == 0) ? 1 : 0;
+    const int grid = std::min(p.pair_tiles ? p.num_tiles / 2 : p.num_tiles, st->sm_count * occ);
+    cudaError_t e = c.k->launch(p, grid, mem != nullptr, tma ? &tmap : nullptr, tma ? &tmap_out : nullptr, tmem, stream);
+    if (e != cudaSuccess) return finish(cuda_fail(e, "kernel launch"));
+    return finish(0);
 }
 }  // namespace
 
 int spectre_mix_fwd(const void *v, int v_dtype, int64_t v_stride_b, int64_t v_stride_n, const void *gate,
                     const void *mem, int64_t mem_stride, void *out, int out_dtype, int64_t out_stride_b,
                     int64_t out_stride_n, int B, int N, int n_fft, int C, int group_width, void *stream) {
-    return mix_fwd_impl(v, v_dtype, v_stride_b, v_stride_n, gate, mem, mem_stride, out, out_dtype, out_stride_b, out_stride_n, B, N,
-                        n_fft, C, group_width, nullptr, 0, stream);
+    return mix_fwd_impl(v, v_dtype, v_stride_b, v_stride_n, gate, nullptr, mem, mem_stride, out, out_dtype, out_stride_b, out_stride_n,
+                        B, N, n_fft, C, group_width, nullptr, 0, stream);
 }
 
 int spectre_mix_fwd_ws(const void *v, int v_dtype, int64_t v_stride_b, int64_t v_stride_n, const void *gate,
@@ -611,8 +654,31 @@ int spectre_mix_fwd_ws(const void *v, int v_dtype, int64_t v_stride_b, int64_t v
                        int64_t out_stride_n, int B, int N, int n_fft, int C, int group_width, void *workspace,
                        size_t workspace_bytes, void *stream) {
     if (!workspace && workspace_bytes) return fail(SPECTRE_MIX_ERR_BAD_ARG, "workspace is null but workspace_bytes = %zu", workspace_bytes);
-    return mix_fwd_impl(v, v_dtype, v_stride_b, v_stride_n, gate, mem, mem_stride, out, out_dtype, out_stride_b, out_stride_n, B, N,
-                        n_fft, C, group_width, workspace, workspace_bytes, stream);
+    return mix_fwd_impl(v, v_dtype, v_stride_b, v_stride_n, gate, nullptr, mem, mem_stride, out, out_dtype, out_stride_b, out_stride_n,
+                        B, N, n_fft, C, group_width, workspace, workspace_bytes, stream);
+}
+
+int spectre_mix_fwd_anchors(const void *v, int v_dtype, int64_t v_stride_b, int64_t v_stride_n, const void *anchors,
+                            const float *bias, const float *eps, const void *pos_phase, int64_t pos_stride_b, int G, int Bk,
+                            const void *mem, int64_t mem_stride, void *out, int out_dtype, int64_t out_stride_b,
+                            int64_t out_stride_n, int B, int N, int n_fft, int C, int group_width, void *workspace,
+                            size_t workspace_bytes, void *stream) {
+    if (!workspace && workspace_bytes) return fail(SPECTRE_MIX_ERR_BAD_ARG, "workspace is null but workspace_bytes = %zu", workspace_bytes);
+    spx::GateSrc gs{reinterpret_cast<const float2 *>(anchors), bias, eps, reinterpret_cast<const float2 *>(pos_phase),
+                    (long long)pos_stride_b, Bk, G};
+    if (n_fft >= 2 && Bk >= 1 && B > 0) {
+        if (int rc = spx::gate_interp_table(n_fft / 2 + 1, Bk, &gs.icoef, &gs.itap)) return rc;
+    }
+    return mix_fwd_impl(v, v_dtype, v_stride_b, v_stride_n, nullptr, &gs, mem, mem_stride, out, out_dtype, out_stride_b, out_stride_n,
+                        B, N, n_fft, C, group_width, workspace, workspace_bytes, stream);
+}
+
+size_t spectre_mix_anchors_workspace_bytes(int v_dtype, int B, int N, int n_fft, int C, int group_width) {
+    const size_t base = spectre_mix_workspace_bytes(v_dtype, B, N, n_fft, C, group_width);
+    if (check_common(B, N, n_fft, C, group_width) || B == 0 || C == 0 || std::min(N, n_fft) == 0) return 0;
+    // layouts the packed kernels cannot take (group width not a multiple of 4) materialise the gate next to the scratch
+    const size_t gate = (group_width % 4 == 0) ? 0 : (size_t)B * (C / group_width) * (n_fft / 2 + 1) * sizeof(float2);
+    return align256(base) + gate;
 }
 
 size_t spectre_mix_workspace_bytes(int v_dtype, int B, int N, int n_fft, int C, int group_width) {

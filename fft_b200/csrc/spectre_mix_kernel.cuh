@@ -37,6 +37,8 @@
 #include <cuda_bf16.h>
 #include <stdint.h>
 
+#include "spectre_gate.cuh"
+
 namespace spx {
 
 enum Mode : int { MODE_QUAD = 0, MODE_PAIR = 1, MODE_REAL = 2 };
@@ -60,6 +62,12 @@ struct MixParams {
     int sched;            // bit 0: stagger also after the barrier before inverse stage 0; bit 1 (TMEM variant): split barrier
                           // around the inverse stage-0 read (arrive after the read, wait before the next tile's stage-0 write)
     unsigned long long *timeline;  // optional: per-CTA phase timestamps (ns) for tools/timeline.py, else nullptr
+    int pair_tiles;       // TMEM variant: a CTA takes the two channel tiles of one gate group back to back (tiles 2P, 2P+1 of pair
+                          // P = blockIdx.x + k gridDim.x) and stages the gate row once for both; the host sets it only when
+                          // tiles_per_row is even and one gate row covers both tiles
+    // ANCH kernels (spectre_mix_fwd_anchors): the gate is never materialised -- the gate staging evaluates
+    // cubic interpolation + modReLU (+ positional phase) of spectre.py:526-536 from the anchors of the row's head
+    GateSrc gsrc;                  // anchors [B][NG][Bk], bias [NG][F_half], eps [NG], optional phase; gate == nullptr
 };
 
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
@@ -659,13 +667,54 @@ __host__ __device__ constexpr int helper_regs(int nt, int minb) {
     return helper_regs_raw(nt, minb, compute_regs(nt, minb)) < 24 ? 24 : helper_regs_raw(nt, minb, compute_regs(nt, minb));
 }
 
+// One gate row (batch row b, gate row g): a pointer into the materialised gate tensor, or (ANCH) the anchors of the row's
+// head from which spx::gate_from_anchors evaluates a bin on demand (spectre.py:526-536 fused into the gate staging).
+template <bool ANCH>
+struct GateRow {
+    const float2 *row;     // !ANCH: gate + (b NG + g) F_half
+    const float2 *a;       // ANCH: anchors of the head, [G][Bk]
+    const float *bias;     // ANCH: modReLU bias of this gate row, [F_half]
+    const float2 *pos;     // ANCH: positional phase row or nullptr
+    const float4 *icoef;   // ANCH: interpolation table (or nullptr)
+    const ushort4 *itap;
+    float eps;
+    int Bk, G, j, F_half;
+    __device__ __forceinline__ float2 at(int k) const {
+        if constexpr (ANCH) return gate_from_anchors_fast(icoef, itap, Bk, G, a, j, k, F_half, __ldg(bias + k), eps, pos);
+        else return __ldg(row + k);
+    }
+};
+template <bool ANCH>
+__device__ __forceinline__ GateRow<ANCH> gate_row(const MixParams &p, int b, int g, int F_half) {
+    GateRow<ANCH> r;
+    if constexpr (ANCH) {
+        const GateSrc &s = p.gsrc;
+        const int head = g / s.G;
+        r.row = nullptr;
+        r.a = s.anchors + ((size_t)b * p.NG + (size_t)head * s.G) * s.Bk;
+        r.bias = s.bias + (size_t)g * F_half;
+        r.pos = s.pos ? s.pos + (size_t)b * s.pos_stride_b : nullptr;
+        r.eps = __ldg(s.eps + g);
+        r.icoef = s.icoef;
+        r.itap = s.itap;
+        r.Bk = s.Bk;
+        r.G = s.G;
+        r.j = g - head * s.G;
+        r.F_half = F_half;
+    } else {
+        r.row = p.gate + ((long long)b * p.NG + g) * F_half;
+        r.a = nullptr; r.bias = nullptr; r.pos = nullptr; r.icoef = nullptr; r.itap = nullptr; r.eps = 0.f; r.Bk = 0; r.G = 1; r.j = 0; r.F_half = F_half;
+    }
+    return r;
+}
+
 // gate row -> registers (all loads in flight), registers -> padded shared table
-template <int N, int NT, int GK>
-__device__ __forceinline__ void gate_fetch(float2 (&gv)[GK], const float2 *gp, int tid) {
+template <int N, int NT, int GK, bool ANCH>
+__device__ __forceinline__ void gate_fetch(float2 (&gv)[GK], const GateRow<ANCH> &gr, int tid) {
 #pragma unroll
     for (int j = 0; j < GK; ++j) {
         const int k = tid + j * NT;
-        gv[j] = (k <= N / 2) ? __ldg(gp + k) : make_float2(0.f, 0.f);
+        gv[j] = (k <= N / 2) ? gr.at(k) : make_float2(0.f, 0.f);
     }
 }
 template <int N, int NT, int GK>
@@ -713,13 +762,13 @@ __device__ __forceinline__ void cta_sync() {
 
 // sub-transform q of a length n_total = R * N transform: bin k' of the sub-spectrum is bin k = q + R k' of the long one;
 // table[k'] = Gfull[k] / n_total with Gfull the Hermitian extension (imag of DC / Nyquist dropped)
-template <int N, int NT, int GKS>
-__device__ __forceinline__ void gate_fetch_sub(float2 (&gv)[GKS], const float2 *gp, int tid, int q, int R) {
+template <int N, int NT, int GKS, bool ANCH>
+__device__ __forceinline__ void gate_fetch_sub(float2 (&gv)[GKS], const GateRow<ANCH> &gr, int tid, int q, int R) {
     const int nt = N * R;
 #pragma unroll
     for (int j = 0; j < GKS; ++j) {
         const int k = q + R * (tid + j * NT);
-        gv[j] = __ldg(gp + (k <= nt / 2 ? k : nt - k));
+        gv[j] = gr.at(k <= nt / 2 ? k : nt - k);
     }
 }
 template <int N, int NT, int GKS>
@@ -741,7 +790,7 @@ __device__ __forceinline__ void gate_put_sub(float2 *gs, const float2 (&gv)[GKS]
 // spectrum.  TMA_IN: the tile is brought into shared memory by TMA (cp.async.bulk.tensor) and the CTA's next
 // tile is prefetched into L2 by the TMA unit; otherwise stage 0 loads straight from global into registers.
 template <class PL, int MODE, int NCOL, int NT, int MINB, class TIN, class TOUT, bool HAS_MEM, bool RFFT_ONLY = false,
-          bool TMA_IN = false, bool TMEM_IO = false>
+          bool TMA_IN = false, bool TMEM_IO = false, bool ANCH = false>
 __global__ void __launch_bounds__(NT + ((TMA_IN && NT >= kSepProducerMinThreads) ? kProducerThreads : 0), MINB)
     spectre_mix_kernel(const MixParams p, const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_out) {
     using E = Elem<MODE>;
@@ -755,6 +804,7 @@ __global__ void __launch_bounds__(NT + ((TMA_IN && NT >= kSepProducerMinThreads)
     constexpr int ITEMS0 = NCOL * L0;                       // stage-0 butterflies per tile
     constexpr int ITERS0 = (ITEMS0 + NT - 1) / NT;          // per thread
     static_assert(!TMA_IN || (MODE == MODE_QUAD && !RFFT_ONLY), "TMA path is built for the packed mix kernel");
+    static_assert(!ANCH || (!RFFT_ONLY && !SPX_GATE_ASYNC), "in-kernel gate generation: mix kernels, register-staged gate rows");
     // stage NS-2 and the middle pass both have radix 16 and >= 32 butterflies per column, items map to threads
     // identically in both (w = tid + k NT): their exchange stays inside a warp
     constexpr bool kWarpLocal = (NS >= 3) && (PL::R(NS - 1) == 16) && (PL::R(NS - 2) == 16) && (NT % 32 == 0) &&
@@ -902,11 +952,18 @@ __global__ void __launch_bounds__(NT + ((TMA_IN && NT >= kSepProducerMinThreads)
             // by the same threads with a box of results, leaves through a TMA store and then takes the next load.  Loads
             // therefore stay in flight while results drain (DEPTH boxes ahead), and the load stream runs across tile
             // boundaries.  Load box idx (stream index over all tiles of this CTA) is consumed at step idx, in slot idx % slots.
-            const int my_tiles = ((int)blockIdx.x < p.num_tiles && !idle) ? (p.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+            // tile sequence of this CTA: tile_of(s), s = 0, 1, ...; paired: tiles 2P, 2P+1 of pair P = blockIdx.x + (s / 2) gridDim.x
+            const bool pair = p.pair_tiles != 0;
+            auto tile_of = [&](int s_) {
+                return pair ? 2 * ((int)blockIdx.x + (s_ >> 1) * (int)gridDim.x) + (s_ & 1) : (int)blockIdx.x + s_ * (int)gridDim.x;
+            };
+            const int units = pair ? p.num_tiles / 2 : p.num_tiles;     // pairs or tiles dealt round robin to the CTAs
+            const int my_units = ((int)blockIdx.x < units && !idle) ? (units - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+            const int my_tiles = pair ? 2 * my_units : my_units;
             const int total_boxes = my_tiles * NBOX;
             // load stream state (used by the elected thread): next box to issue, kept incrementally -- the elected thread's
             // path between two barriers is the helper's critical path, so no divisions there except once per tile
-            int ld_left = total_boxes, ld_k = 0, ld_t = (int)blockIdx.x, ld_tb = 0, ld_tc = 0;
+            int ld_left = total_boxes, ld_k = 0, ld_t = tile_of(0), ld_tb = 0, ld_tc = 0, ld_seq = 0;
             uint32_t ld_slot = 0;
             if (my_tiles > 0) {
                 ld_tb = ld_t / p.tiles_per_row;
@@ -921,7 +978,7 @@ __global__ void __launch_bounds__(NT + ((TMA_IN && NT >= kSepProducerMinThreads)
                 ld_slot = (ld_slot + 1 == kTmemSlots) ? 0 : ld_slot + 1;
                 if (++ld_k == NBOX) {
                     ld_k = 0;
-                    ld_t += (int)gridDim.x;
+                    ld_t = tile_of(++ld_seq);
                     ld_tb = ld_t / p.tiles_per_row;
                     ld_tc = (ld_t - ld_tb * p.tiles_per_row) * NCOL * CH;
                 }
@@ -936,7 +993,7 @@ __global__ void __launch_bounds__(NT + ((TMA_IN && NT >= kSepProducerMinThreads)
 #endif
             if (hl == kLoadLane) {
                 for (int i = 0; i < kDepth && ld_left > 0; ++i) issue_next();
-                if (p.prefetch == 1 && my_tiles > 1) prefetch_tile((int)blockIdx.x + (int)gridDim.x);
+                if (p.prefetch == 1 && my_tiles > 1) prefetch_tile(tile_of(1));
             }
             // prefetch == 2: the four CTAs that work on four adjacent channel tiles pull the NEXT tiles' rows into L2 as whole
             // 128-byte lines (one quarter of the rows each), so DRAM sees full-line reads instead of 32-byte pieces
@@ -960,18 +1017,18 @@ __global__ void __launch_bounds__(NT + ((TMA_IN && NT >= kSepProducerMinThreads)
                 if (do_park && P >= 1) mbar_wait(bar_in_free, (P - 1) & 1);    // compute warps pulled tile P-1 out of TMEM-IN
                 if (do_drain) mbar_wait(bar_out_full, (P - 2) & 1);            // results of tile P-2 sit in TMEM-OUT
                 tc_fence_after();
-                if (p.prefetch == 1 && hl == kLoadLane && P + 2 < my_tiles) prefetch_tile((int)blockIdx.x + (P + 2) * (int)gridDim.x);
+                if (p.prefetch == 1 && hl == kLoadLane && P + 2 < my_tiles) prefetch_tile(tile_of(P + 2));
 #if SPX_HELPER_TL
                 if (tl_on) tl[1] = globaltimer_ns();
 #endif
-                const int td = (int)blockIdx.x + (P - 2) * (int)gridDim.x;
+                const int td = do_drain ? tile_of(P - 2) : 0;
                 const int tb = do_drain ? td / p.tiles_per_row : 0;
                 const int tc = do_drain ? (td - tb * p.tiles_per_row) * NCOL * CH : 0;
                 // cooperative prefetch target: rows of this CTA's tile P + 1 (its loads are issued one phase from now)
 #if SPX_COOP_PF
                 const TIN *pf = nullptr;
                 if (coop_pf && P + 1 < my_tiles) {
-                    const int tp = (int)blockIdx.x + (P + 1) * (int)gridDim.x;
+                    const int tp = tile_of(P + 1);
                     const int pb = tp / p.tiles_per_row, pc = tp - pb * p.tiles_per_row;
                     pf = vbase + (long long)pb * p.v_sb + (long long)((pc & 3) * 64 + hl) * p.v_sn + (pc & ~3) * (NCOL * CH);
                 }
@@ -1099,14 +1156,27 @@ __global__ void __launch_bounds__(NT + ((TMA_IN && NT >= kSepProducerMinThreads)
 
     // tile -> (row of the [B'][n_fft][C] tensor, channel-tile column), advanced incrementally: integer divisions sit on every
     // warp's serial path between two tiles, so the loop has none (group index by shift when group_width is a power of two)
-    const int step_row = (int)gridDim.x / p.tiles_per_row, step_col = (int)gridDim.x - step_row * p.tiles_per_row;
-    int brow = (int)blockIdx.x / p.tiles_per_row, tcol = (int)blockIdx.x - brow * p.tiles_per_row;
-    int nrow_ = 0, ncol_ = 0;
+    // Paired order (TMEM variant, p.pair_tiles): tiles 2P and 2P+1 of pair P = blockIdx.x + k gridDim.x back to back -- the two
+    // channel tiles of one gate group, so the gate row is staged (or, ANCH, generated) once per pair.
+    const bool pair = TMEM_IO && p.pair_tiles != 0;
+    const int stride = pair ? 2 * (int)gridDim.x : (int)gridDim.x;
+    const int step_row = stride / p.tiles_per_row, step_col = stride - step_row * p.tiles_per_row;
+    const int first_tile = pair ? 2 * (int)blockIdx.x : (int)blockIdx.x;
+    int brow = first_tile / p.tiles_per_row, tcol = first_tile - brow * p.tiles_per_row;
+    int nrow_ = 0, ncol_ = 0, tile_next_ = 0, seq = 0;
     auto gdiv = [&](int x) { return p.gw_shift >= 0 ? (x >> p.gw_shift) : x / p.group_width; };
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, brow = nrow_, tcol = ncol_) {
-        nrow_ = brow + step_row;
-        ncol_ = tcol + step_col;
-        if (ncol_ >= p.tiles_per_row) { ncol_ -= p.tiles_per_row; ++nrow_; }
+    for (int tile = first_tile; tile < p.num_tiles; tile = tile_next_, brow = nrow_, tcol = ncol_, ++seq) {
+        const bool partner_next = pair && !(seq & 1);   // the next tile is the second half of this pair: same row, same gate row
+        if (partner_next) {
+            nrow_ = brow;
+            ncol_ = tcol + 1;
+            tile_next_ = tile + 1;
+        } else {
+            nrow_ = brow + step_row;
+            ncol_ = tcol + step_col - (pair ? 1 : 0);
+            tile_next_ = tile + stride - (pair ? 1 : 0);
+            if (ncol_ >= p.tiles_per_row) { ncol_ -= p.tiles_per_row; ++nrow_; }
+        }
         const int b = SUB ? (brow >> p.sub_shift) : brow;        // batch row (gate / memory)
         const int qsub = SUB ? (brow & (p.sub_R - 1)) : 0;       // which interleaved sub-transform
         const int ce0 = tcol * NCOL;                             // first element column of the tile
@@ -1119,12 +1189,12 @@ __global__ void __launch_bounds__(NT + ((TMA_IN && NT >= kSepProducerMinThreads)
         // With one table per tile this was already started while the previous tile finished (see below); else do it here.
         if constexpr (!RFFT_ONLY) {
             if constexpr (SUB) {
-                if (tile == (int)blockIdx.x) {
+                if (seq == 0) {
                     float2 gv[GKS];
-                    gate_fetch_sub<N, NT, GKS>(gv, p.gate + ((long long)b * p.NG + g0) * ((N * p.sub_R) / 2 + 1), tid, qsub, p.sub_R);
+                    gate_fetch_sub<N, NT, GKS>(gv, gate_row<ANCH>(p, b, g0, (N * p.sub_R) / 2 + 1), tid, qsub, p.sub_R);
                     gate_put_sub<N, NT, GKS>(gate_s, gv, tid, qsub, p.sub_R, p.inv_n);
                 }
-            } else if (!gate_early || tile == (int)blockIdx.x) {
+            } else if (!gate_early || seq == 0) {
                 for (int t = 0; t < p.gate_tables; ++t) {
                     const int g = g0 + t;
                     if (g < p.NG) {
@@ -1132,7 +1202,7 @@ __global__ void __launch_bounds__(NT + ((TMA_IN && NT >= kSepProducerMinThreads)
                         gate_copy_async<N, NT, GK>(gate_s + t * GS, p.gate + ((long long)b * p.NG + g) * (N / 2 + 1), tid);
 #else
                         float2 gv[GK];
-                        gate_fetch<N, NT, GK>(gv, p.gate + ((long long)b * p.NG + g) * (N / 2 + 1), tid);
+                        gate_fetch<N, NT, GK>(gv, gate_row<ANCH>(p, b, g, N / 2 + 1), tid);
                         gate_put<N, NT, GK>(gate_s + t * GS, gv, tid, p.inv_n);
 #endif
                     }
@@ -1332,19 +1402,17 @@ __global__ void __launch_bounds__(NT + ((TMA_IN && NT >= kSepProducerMinThreads)
         // the gate table is free again: start fetching the next tile's gate row, park it in registers
         // across the inner inverse passes, and publish it before the last pass
         float2 gnext[SUB ? GKS : (SPX_GATE_ASYNC ? 1 : GK)];
-        const int tile_next = tile + gridDim.x;
-        const bool fetch_next = gate_early && tile_next < p.num_tiles;
+        const bool fetch_next = gate_early && tile_next_ < p.num_tiles && !partner_next;   // the partner tile reuses the table
         int nq = 0;
         if (fetch_next) {
             const int nrow = nrow_;
             const int ng = gdiv(ncol_ * NCOL * CH);
             if constexpr (SUB) {
                 nq = nrow & (p.sub_R - 1);
-                gate_fetch_sub<N, NT, GKS>(gnext, p.gate + ((long long)(nrow >> p.sub_shift) * p.NG + ng) * ((N * p.sub_R) / 2 + 1), tid, nq,
-                                           p.sub_R);
+                gate_fetch_sub<N, NT, GKS>(gnext, gate_row<ANCH>(p, nrow >> p.sub_shift, ng, (N * p.sub_R) / 2 + 1), tid, nq, p.sub_R);
             } else {
 #if !SPX_GATE_ASYNC
-                gate_fetch<N, NT, GK>(gnext, p.gate + ((long long)nrow * p.NG + ng) * (N / 2 + 1), tid);
+                gate_fetch<N, NT, GK>(gnext, gate_row<ANCH>(p, nrow, ng, N / 2 + 1), tid);
 #endif
             }
         }

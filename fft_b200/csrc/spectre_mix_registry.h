@@ -20,12 +20,14 @@ struct KernelEntry {
     size_t (*smem_bytes)(int gate_tables, bool tma, bool tmem);
     int out_box_rows;   // rows per TMA store box (TMA variant)
     // tmap != nullptr selects the TMA-fed variant (only when tma_ok)
+    // p.gate == nullptr selects the in-kernel gate generator (p.gsrc = anchors; only when anch_ok)
     cudaError_t (*launch)(const MixParams &p, int grid, bool has_mem, const CUtensorMap *tmap_in, const CUtensorMap *tmap_out,
                           bool tmem, cudaStream_t st);
     int (*occupancy)(int gate_tables, bool has_mem, bool tma, bool tmem);
     int tma_ok;    // 1: a TMA-fed variant exists (packed mode, landed row >= 16 bytes)
     int tmem_ok;   // 1: a TMEM-staged variant exists (tile I/O parked in tensor memory by a helper warpgroup)
     int sub;       // 1: sub-transform variant of the long-context two-pass path (complex input, strided gate gather)
+    int anch_ok;   // 1: variants that evaluate the gate from anchors inside the gate staging exist (packed mode)
     // forward half only (half spectrum out); MODE_REAL variants only, else nullptr
     cudaError_t (*launch_rfft)(const MixParams &p, int grid, cudaStream_t st);
 };
@@ -41,12 +43,20 @@ struct Launcher {
     // TMEM staging: packed tiles (fp32 or bf16 in HBM, fp32 in tensor memory), one stage-0 butterfly per thread, 1 CTA per SM, two tiles fit the 512 columns
     static constexpr bool kTmem = kTma && NT >= kSepProducerMinThreads && NT == NCOL * PL::L(0) &&
                                   PL::L(0) % 128 == 0 && MINB == 1 && (PL::N * NCOL * 4 / 128 * 2 <= 512);
-    template <bool HAS_MEM, bool TMA, bool TMEM>
+    // in-kernel gate generation (spectre_mix_fwd_anchors): built for the packed mode, the layout of every Spectre model with
+    // 4 | group_width; other layouts take the materialised-gate kernels behind spectre_gate_expand
+    static constexpr bool kAnch = (MODE == MODE_QUAD);
+    template <bool HAS_MEM, bool TMA, bool TMEM, bool ANCH = false>
     static const void *fn() {
         return reinterpret_cast<const void *>(
-            &spectre_mix_kernel<PL, MODE, NCOL, NT, MINB, TIO, TIO, HAS_MEM, false, (TMA && kTma), (TMA && TMEM && kTmem)>);
+            &spectre_mix_kernel<PL, MODE, NCOL, NT, MINB, TIO, TIO, HAS_MEM, false, (TMA && kTma), (TMA && TMEM && kTmem), (ANCH && kAnch)>);
     }
-    static const void *pick(bool has_mem, bool tma, bool tmem = false) {
+    static const void *pick(bool has_mem, bool tma, bool tmem = false, bool anch = false) {
+        if (anch && kAnch) {
+            if (tma && tmem && kTmem) return has_mem ? fn<true, true, true, true>() : fn<false, true, true, true>();
+            if (tma && kTma) return has_mem ? fn<true, true, false, true>() : fn<false, true, false, true>();
+            return has_mem ? fn<true, false, false, true>() : fn<false, false, false, true>();
+        }
         if (tma && tmem && kTmem) return has_mem ? fn<true, true, true>() : fn<false, true, true>();
         if (tma && kTma) return has_mem ? fn<true, true, false>() : fn<false, true, false>();
         return has_mem ? fn<true, false, false>() : fn<false, false, false>();
@@ -54,7 +64,7 @@ struct Launcher {
     static cudaError_t launch(const MixParams &p, int grid, bool has_mem, const CUtensorMap *tmap, const CUtensorMap *tmap_out,
                               bool tmem, cudaStream_t st) {
         const size_t sm = smem_bytes(p.gate_tables, tmap != nullptr, tmem);
-        const void *f = pick(has_mem, tmap != nullptr, tmem);
+        const void *f = pick(has_mem, tmap != nullptr, tmem, p.gate == nullptr);
         // opt in to > 48 KB dynamic shared memory (cheap; the driver caches the attribute per function)
         cudaError_t e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
         if (e != cudaSuccess) return e;
@@ -114,6 +124,7 @@ struct RfftPtr<PL, MODE_REAL, NCOL, NT, MINB, TIO> {
             &::spx::Launcher<::spx::Plan<R0, R1, R2, R3>, MODE, NCOL, NT, MINB, TIO>::occupancy,              \
             ::spx::Launcher<::spx::Plan<R0, R1, R2, R3>, MODE, NCOL, NT, MINB, TIO>::kTma ? 1 : 0,            \
             ::spx::Launcher<::spx::Plan<R0, R1, R2, R3>, MODE, NCOL, NT, MINB, TIO>::kTmem ? 1 : 0, 0,        \
+            ::spx::Launcher<::spx::Plan<R0, R1, R2, R3>, MODE, NCOL, NT, MINB, TIO>::kAnch ? 1 : 0,           \
             ::spx::RfftPtr<::spx::Plan<R0, R1, R2, R3>, MODE, NCOL, NT, MINB, TIO>::get()                     \
     }
 
@@ -127,6 +138,7 @@ struct RfftPtr<PL, MODE_REAL, NCOL, NT, MINB, TIO> {
             &::spx::Launcher<::spx::Plan<R0, R1, R2, R3, true>, MODE, NCOL, NT, MINB, TIO>::occupancy,        \
             ::spx::Launcher<::spx::Plan<R0, R1, R2, R3, true>, MODE, NCOL, NT, MINB, TIO>::kTma ? 1 : 0,      \
             ::spx::Launcher<::spx::Plan<R0, R1, R2, R3, true>, MODE, NCOL, NT, MINB, TIO>::kTmem ? 1 : 0, 1,  \
+            ::spx::Launcher<::spx::Plan<R0, R1, R2, R3, true>, MODE, NCOL, NT, MINB, TIO>::kAnch ? 1 : 0,     \
             nullptr                                                                                           \
     }
 

@@ -21,6 +21,14 @@ def shard_rows(total_rows: int, rank: int, world: int) -> Tuple[int, int]:
     return begin, begin + base + (1 if rank < rem else 0)
 
 
+def micro_batches(rows: int, micro_batch: int):
+    """[begin, end) spans that stream ``rows`` local rows through reused buffers in launches of at most ``micro_batch``
+    rows (SURVEY 8e memory caveat: 206 GB of I/O tensors at batch 8192 do not fit one GPU)."""
+    if micro_batch <= 0:
+        raise ValueError(f"bad micro_batch {micro_batch}")
+    return [(r0, min(r0 + micro_batch, rows)) for r0 in range(0, rows, micro_batch)]
+
+
 def reduce_measurement(elapsed_ms: float, units: int, checksum: float, device=None):
     """(max elapsed over ranks, total units, summed checksum): the whole-job view of a sharded run.
 

@@ -21,7 +21,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from .ops import gate_expand, spectral_mix
+from .ops import gate_expand, spectral_mix, spectral_mix_anchors
 
 try:  # optional, like the reference (spectre.py:10-14)
     import torch_dct as _dct
@@ -203,11 +203,26 @@ def head_project_and_gate(head, x: torch.Tensor, pos_phase: Optional[torch.Tenso
     return V, gate_half, q_pool
 
 
+def head_anchors(head, Q: torch.Tensor):
+    """spectre.py:511-516 of one head: pooled descriptor -> q_norm -> gate MLP -> anchors (B, G, Bk) complex64, and q_pool."""
+    q_pool = head.q_norm(head.pooling(Q))
+    anchors = head.gate_mlp(q_pool).float().view(q_pool.shape[0], head.G, head.B, 2)
+    return torch.view_as_complex(anchors.contiguous()), q_pool
+
+
 def head_forward(head, x, pos_phase=None, return_q_pool=False, memory_fft=None):
-    """``SpectreHead.forward`` (spectre.py:479-557) with :506, :542-553 replaced by the fused kernel."""
+    """``SpectreHead.forward`` (spectre.py:479-557) with :506, :526-553 replaced by ONE fused kernel: the gate generator's
+    tail (interpolation, modReLU, phase) is evaluated inside the mix kernel from the anchors."""
     assert x.shape[-1] == head.d
-    V, gate_half, q_pool = head_project_and_gate(head, x, pos_phase)
-    mixed = spectral_mix(V, gate_half, memory_fft, n_fft=head.n_fft, group_width=head.d_g)
+    if x.is_cuda and not head.use_toeplitz:
+        V = head.W_v(x)
+        anchors, q_pool = head_anchors(head, head.W_q(x))
+        mixed = spectral_mix_anchors(V, anchors, head.modrelu.bias.view(head.G, head.F_half),
+                                     head.modrelu.eps.reshape(1).expand(head.G), pos_phase, memory_fft,
+                                     n_fft=head.n_fft, group_width=head.d_g, G=head.G)
+    else:
+        V, gate_half, q_pool = head_project_and_gate(head, x, pos_phase)
+        mixed = spectral_mix(V, gate_half, memory_fft, n_fft=head.n_fft, group_width=head.d_g)
     result = head.dropout(mixed)
     return (result, q_pool) if return_q_pool else result
 
@@ -241,12 +256,12 @@ def _heads_batchable(mh) -> bool:
                and len(h.gate_mlp) == 3 and h.q_norm.eps == h0.q_norm.eps for h in mh.heads)
 
 
-def multihead_gate(mh, Q_all: torch.Tensor, pos_phase: Optional[torch.Tensor]):
-    """Gate generator of ALL heads at once (spectre.py:511-536 evaluated H times by the loop of :712-713).
+def multihead_anchors(mh, Q_all: torch.Tensor):
+    """spectre.py:511-516 of ALL heads at once (evaluated H times by the loop of :712-713).
 
     Q_all (B, N, H, d_h).  Pooled descriptor -> per-head LayerNorm -> per-head 2-layer MLP as two batched GEMMs over the
-    stacked head weights -> anchors (B, H*G, Bk) -> ONE ``gate_expand`` launch (cubic interpolation, modReLU, phase).
-    Returns gate (B, H*G, F_half) complex64 and q_pool (B, H*d_h), the concatenation of :718-719.
+    stacked head weights.  Returns anchors (B, H*G, Bk) complex64, the stacked modReLU bias (H*G, F_half) and eps (H*G,),
+    and q_pool (B, H*d_h), the concatenation of :718-719.
     """
     heads, h0 = mh.heads, mh.heads[0]
     H, G, Bk, F_half = len(heads), h0.G, h0.B, h0.F_half
@@ -263,8 +278,16 @@ def multihead_gate(mh, Q_all: torch.Tensor, pos_phase: Optional[torch.Tensor]):
     anchors = torch.view_as_complex(anc.float().reshape(Bsz, H * G, Bk, 2).contiguous())  # :516
     bias = _stacked(mh, "modrelu.bias").reshape(H * G, F_half)
     eps = _stacked(mh, "modrelu.eps").reshape(H).repeat_interleave(G)
-    gate = gate_expand(anchors, bias, eps, pos_phase, F_half=F_half, G=G)                    # :526-536
-    return gate, qn.reshape(Bsz, H * h0.d)
+    return anchors, bias, eps, qn.reshape(Bsz, H * h0.d)
+
+
+def multihead_gate(mh, Q_all: torch.Tensor, pos_phase: Optional[torch.Tensor]):
+    """Gate generator of ALL heads, materialised: :func:`multihead_anchors` then ONE ``gate_expand`` launch (cubic
+    interpolation, modReLU, phase; spectre.py:526-536).  Returns gate (B, H*G, F_half) complex64 and q_pool (B, H*d_h).
+    The forward path does not call this any more (the mix kernel evaluates the gate from the anchors itself)."""
+    anchors, bias, eps, q_pool = multihead_anchors(mh, Q_all)
+    h0 = mh.heads[0]
+    return gate_expand(anchors, bias, eps, pos_phase, F_half=h0.F_half, G=h0.G), q_pool
 
 
 def multihead_forward(mh, x, pos_phase=None, memory_fft=None):
@@ -282,7 +305,10 @@ def multihead_forward(mh, x, pos_phase=None, memory_fft=None):
     V_all = torch.einsum("bnhi,hoi->bnho", xh, _stacked(mh, "W_v.weight")).reshape(B, N, d)   # head h = channels [h*d_h, (h+1)*d_h)
     Q_all = torch.einsum("bnhi,hoi->bnho", xh, _stacked(mh, "W_q.weight"))                    # (B, N, H, d_h)
     if x.is_cuda and _heads_batchable(mh):
-        gate_all, q_pool = multihead_gate(mh, Q_all, pos_phase)
+        # gate generator tail fused into the mix kernel: anchors in, no (B, H*G, F_half) gate tensor
+        anchors, bias, eps, q_pool = multihead_anchors(mh, Q_all)
+        mixed = spectral_mix_anchors(V_all, anchors, bias, eps, pos_phase, memory_fft, n_fft=h0.n_fft, group_width=h0.d_g, G=h0.G)
+        gate_all = None
     else:
         gates, pools = [], []
         for i, h in enumerate(mh.heads):
@@ -291,7 +317,8 @@ def multihead_forward(mh, x, pos_phase=None, memory_fft=None):
             pools.append(qp)
         gate_all = torch.cat(gates, dim=1)         # (B, H*G, F_half)
         q_pool = torch.cat(pools, dim=-1)
-    mixed = spectral_mix(V_all, gate_all, memory_fft, n_fft=h0.n_fft, group_width=h0.d_g)
+    if gate_all is not None:
+        mixed = spectral_mix(V_all, gate_all, memory_fft, n_fft=h0.n_fft, group_width=h0.d_g)
     if not isinstance(h0.dropout, nn.Identity):  # per-head dropout modules, applied on their slices (:553)
         mixed = torch.cat([h.dropout(m) for h, m in zip(mh.heads, torch.chunk(mixed, H, dim=-1))], dim=-1)
     return mh.out_proj(mh.wavelet_refinement(mixed, q_pool))

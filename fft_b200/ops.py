@@ -182,8 +182,8 @@ def rfft_seq(V: torch.Tensor, n_fft: int) -> torch.Tensor:
 
 
 # ----------------------------------------------------------------------------- gate generator tail
-def _gate_expand_impl(anchors: torch.Tensor, bias: torch.Tensor, eps: torch.Tensor, pos_phase: Optional[torch.Tensor],
-                      F_half: int, G: int) -> torch.Tensor:
+def _gate_args(anchors, bias, eps, pos_phase, F_half: int, G: int):
+    """Validate / normalise the gate generator's inputs; returns (anchors, bias, eps, pos_phase or None, pos_stride_b)."""
     _require_cuda(anchors, "anchors")
     if anchors.dim() != 3 or not anchors.is_complex():
         raise ValueError(f"anchors must be complex (B, NG, Bk), got {tuple(anchors.shape)} {anchors.dtype}")
@@ -197,7 +197,7 @@ def _gate_expand_impl(anchors: torch.Tensor, bias: torch.Tensor, eps: torch.Tens
     anchors = anchors.to(torch.complex64).contiguous()
     bias = bias.to(device=anchors.device, dtype=torch.float32).contiguous()
     eps = eps.to(device=anchors.device, dtype=torch.float32).contiguous()
-    pos_ptr, pos_stride = None, 0
+    pos_stride = 0
     if pos_phase is not None:
         pos_phase = pos_phase.to(device=anchors.device, dtype=torch.complex64)
         if pos_phase.dim() == 1:
@@ -205,7 +205,15 @@ def _gate_expand_impl(anchors: torch.Tensor, bias: torch.Tensor, eps: torch.Tens
         if pos_phase.dim() != 2 or pos_phase.shape[-1] != F_half or pos_phase.shape[0] not in (1, B):
             raise ValueError(f"pos_phase must be (F_half,), (1, F_half) or (B, F_half), got {tuple(pos_phase.shape)}")
         pos_phase = pos_phase.contiguous()
-        pos_ptr, pos_stride = pos_phase.data_ptr(), (F_half if pos_phase.shape[0] == B and B > 1 else 0)
+        pos_stride = F_half if pos_phase.shape[0] == B and B > 1 else 0
+    return anchors, bias, eps, pos_phase, pos_stride
+
+
+def _gate_expand_impl(anchors: torch.Tensor, bias: torch.Tensor, eps: torch.Tensor, pos_phase: Optional[torch.Tensor],
+                      F_half: int, G: int) -> torch.Tensor:
+    anchors, bias, eps, pos_phase, pos_stride = _gate_args(anchors, bias, eps, pos_phase, F_half, G)
+    B, NG, Bk = anchors.shape
+    pos_ptr = None if pos_phase is None else pos_phase.data_ptr()
     gate = torch.empty((B, NG, F_half), dtype=torch.complex64, device=anchors.device)
     if gate.numel():
         lib = _lib.load()
@@ -267,6 +275,110 @@ def gate_expand(anchors: torch.Tensor, bias: torch.Tensor, eps: torch.Tensor, po
     """
     _require_cuda(anchors, "anchors")
     return _GateExpand.apply(anchors, bias, eps, pos_phase, int(F_half), int(G))
+
+
+# ----------------------------------------------------------------------------- mix with the gate generator fused in (8f-2)
+def _mix_anchors_impl(V, anchors, bias, eps, pos_phase, memory, n_fft: int, group_width: int, G: int) -> torch.Tensor:
+    _require_cuda(V, "V")
+    if V.dim() != 3:
+        raise ValueError(f"V must be (B, N, C), got {tuple(V.shape)}")
+    if V.dtype not in _DT:
+        raise TypeError(f"V dtype {V.dtype} unsupported (float32 or bfloat16)")
+    B, N, C = V.shape
+    F_half = n_fft // 2 + 1
+    if group_width <= 0 or C % group_width:
+        raise ValueError(f"C={C} is not a multiple of group_width={group_width}")
+    NG = C // group_width
+    anchors, bias, eps, pos_phase, pos_stride = _gate_args(anchors, bias, eps, pos_phase, F_half, G)
+    if tuple(anchors.shape[:2]) != (B, NG):
+        raise ValueError(f"anchors must be (B, C/group_width, Bk) = ({B}, {NG}, Bk), got {tuple(anchors.shape)}")
+    V = _rows_last_contig(V)
+    es = V.element_size()
+    if group_width % 4 == 0 and (V.data_ptr() % (4 * es) or V.stride(0) % 4 or V.stride(1) % 4):
+        V = V.contiguous()      # keep the packed layout (the one with the fused gate generator) reachable
+    mem_ptr, mem_stride = None, 0
+    if memory is not None:
+        if tuple(memory.shape) != (F_half, C):
+            raise ValueError(f"memory must be (n_fft/2+1, C) = {(F_half, C)}, got {tuple(memory.shape)}")
+        memory = _rows_last_contig(memory.to(device=V.device, dtype=torch.complex64))
+        mem_ptr, mem_stride = memory.data_ptr(), memory.stride(0)
+    out = torch.empty((B, min(N, n_fft), C), dtype=V.dtype, device=V.device)
+    if out.numel() == 0:
+        return out
+    lib = _lib.load()
+    with torch.cuda.device(V.device):
+        ws_bytes = lib.spectre_mix_anchors_workspace_bytes(_DT[V.dtype], B, N, n_fft, C, group_width)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=V.device) if ws_bytes else None
+        stream = torch.cuda.current_stream(V.device).cuda_stream
+        rc = lib.spectre_mix_fwd_anchors(
+            V.data_ptr(), _DT[V.dtype], V.stride(0), V.stride(1),
+            anchors.data_ptr(), bias.data_ptr(), eps.data_ptr(), None if pos_phase is None else pos_phase.data_ptr(), pos_stride,
+            G, anchors.shape[2], mem_ptr, mem_stride,
+            out.data_ptr(), _DT[out.dtype], out.stride(0), out.stride(1),
+            B, N, n_fft, C, group_width, ws.data_ptr() if ws is not None else None, ws_bytes, ctypes.c_void_p(stream),
+        )
+    _lib.check(rc, "spectral_mix_anchors")
+    return out
+
+
+@torch.library.custom_op("fft_b200::spectral_mix_anchors", mutates_args=(), device_types="cuda")
+def _spectral_mix_anchors_op(V: torch.Tensor, anchors: torch.Tensor, bias: torch.Tensor, eps: torch.Tensor,
+                             pos_phase: Optional[torch.Tensor], memory: Optional[torch.Tensor], n_fft: int, group_width: int,
+                             G: int) -> torch.Tensor:
+    return _mix_anchors_impl(V, anchors, bias, eps, pos_phase, memory, n_fft, group_width, G)
+
+
+@_spectral_mix_anchors_op.register_fake
+def _(V, anchors, bias, eps, pos_phase, memory, n_fft, group_width, G):
+    B, N, C = V.shape
+    return V.new_empty((B, min(N, n_fft), C))
+
+
+def _mix_anchors_setup_context(ctx, inputs, output):
+    V, anchors, bias, eps, pos_phase, memory, n_fft, group_width, G = inputs
+    ctx.n_fft, ctx.group_width, ctx.G = n_fft, group_width, G
+    ctx.has_memory = memory is not None
+    ctx.save_for_backward(V, anchors, bias, eps, pos_phase)
+
+
+def _mix_anchors_backward(ctx, dY):
+    """Backward of the fused op = backward of ``spectral_mix`` chained with the gate generator's: the gate is materialised
+    here (backward only), d gate comes from the mix adjoint, and anchors / bias receive it through the stock-op formula."""
+    V, anchors, bias, eps, pos_phase = ctx.saved_tensors
+    F_half = ctx.n_fft // 2 + 1
+    need_gate_grads = ctx.needs_input_grad[1] or ctx.needs_input_grad[2]
+    with torch.enable_grad():
+        a = anchors.detach().requires_grad_(ctx.needs_input_grad[1])
+        b = bias.detach().requires_grad_(ctx.needs_input_grad[2])
+        if need_gate_grads:
+            gate = _gate_expand_torch(a, b, eps, pos_phase, F_half, ctx.G)
+        else:
+            gate = _gate_expand_impl(anchors, bias, eps, pos_phase, F_half, ctx.G)
+    inner = type("Ctx", (), {})()
+    inner.n_fft, inner.group_width, inner.N, inner.has_memory = ctx.n_fft, ctx.group_width, V.shape[1], ctx.has_memory
+    inner.saved_tensors = (V, gate.detach())
+    inner.needs_input_grad = (ctx.needs_input_grad[0], need_gate_grads, ctx.needs_input_grad[5], False, False)
+    dV, dgate, dmem, _, _ = _mix_backward(inner, dY)
+    da = db = None
+    if need_gate_grads:
+        wanted = [t for t, need in ((a, ctx.needs_input_grad[1]), (b, ctx.needs_input_grad[2])) if need]
+        grads = list(torch.autograd.grad(gate, wanted, dgate))
+        da = grads.pop(0) if ctx.needs_input_grad[1] else None
+        db = grads.pop(0) if ctx.needs_input_grad[2] else None
+    return dV, da, db, None, None, dmem, None, None, None
+
+
+_spectral_mix_anchors_op.register_autograd(_mix_anchors_backward, setup_context=_mix_anchors_setup_context)
+
+
+def spectral_mix_anchors(V: torch.Tensor, anchors: torch.Tensor, bias: torch.Tensor, eps: torch.Tensor,
+                         pos_phase: Optional[torch.Tensor] = None, memory: Optional[torch.Tensor] = None, *,
+                         n_fft: int, group_width: int, G: int) -> torch.Tensor:
+    """``spectral_mix(V, gate_expand(anchors, bias, eps, pos_phase), memory)`` in ONE launch: the gate generator's tail
+    (``spectre.py:526-536``) is evaluated inside the mix kernel's gate staging and the ``(B, NG, F_half)`` gate is never
+    materialised.  Arguments as :func:`gate_expand` and :func:`spectral_mix`."""
+    _require_cuda(V, "V")
+    return _spectral_mix_anchors_op(V, anchors, bias, eps, pos_phase, memory, int(n_fft), int(group_width), int(G))
 
 
 def spectral_mix_host(V: torch.Tensor, gate: torch.Tensor, memory: Optional[torch.Tensor] = None, *,

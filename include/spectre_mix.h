@@ -86,6 +86,23 @@ int spectre_mix_fwd_ws(const void *v, int v_dtype, int64_t v_stride_b, int64_t v
                        int B, int N, int n_fft, int C, int group_width,
                        void *workspace, size_t workspace_bytes, void *stream);
 
+/* The same mix with the gate generator's tail FUSED into the kernel: instead of a materialised gate the call
+ * takes the anchors and evaluates, inside the kernel's gate staging, for the gate row g of batch row b at bin k
+ *   gate[b, g, k] = modReLU_g( cubic_interp(planes of anchors[b, head(g)])(k) ) * pos_phase[b or 0, k]
+ * (spectre.py:526-528 -> :26-61 grid_sample bicubic / border / align_corners, :531 -> :109-121, :534-536; arguments as
+ * spectre_gate_expand below), then proceeds as spectre_mix_fwd (spectre.py:506, :542-553).  The (B, NG, F_half) gate tensor
+ * is never written or read: algorithmic bytes drop to V + out + anchors + bias.  Layouts the packed kernels cannot take
+ * (group_width not a multiple of 4, misaligned rows) expand the gate into the workspace first and run the plain kernels.
+ * workspace >= spectre_mix_anchors_workspace_bytes(...) or NULL (stream-ordered internal allocation when needed). */
+size_t spectre_mix_anchors_workspace_bytes(int v_dtype, int B, int N, int n_fft, int C, int group_width);
+int spectre_mix_fwd_anchors(const void *v, int v_dtype, int64_t v_stride_b, int64_t v_stride_n,
+                            const void *anchors, const float *bias, const float *eps,
+                            const void *pos_phase, int64_t pos_stride_b, int G, int Bk,
+                            const void *mem, int64_t mem_stride,
+                            void *out, int out_dtype, int64_t out_stride_b, int64_t out_stride_n,
+                            int B, int N, int n_fft, int C, int group_width,
+                            void *workspace, size_t workspace_bytes, void *stream);
+
 /* Same function on HOST buffers (what a non-CUDA host language binds): copies
  * v/gate/mem to the device in batch chunks, runs the kernel and copies the
  * result back, overlapping the three on internal streams; returns when `out`

@@ -11,7 +11,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from fft_b200.dist import reduce_measurement, shard_rows
+from fft_b200.dist import micro_batches, reduce_measurement, shard_rows
 
 
 def test_shard_rows_cover_batch_exactly():
@@ -22,6 +22,20 @@ def test_shard_rows_cover_batch_exactly():
             assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
             sizes = [e - b for b, e in spans]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_cfg5_strong_scaling_plan():
+    """BASELINE.json configs[4]: 8192 rows over 1/2/4/8 ranks, each rank streaming micro-batches of <= 148 rows: every row of
+    the global batch is processed exactly once per step at every world size."""
+    for world in (1, 2, 4, 8):
+        seen = []
+        for r in range(world):
+            b0, b1 = shard_rows(8192, r, world)
+            spans = micro_batches(b1 - b0, 148)
+            assert all(0 < e - b <= 148 for b, e in spans)
+            assert spans[0][0] == 0 and spans[-1][1] == b1 - b0 and all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            seen += [b0 + i for b, e in spans for i in range(b, e)]
+        assert seen == list(range(8192))
 
 
 def _free_port():

@@ -187,3 +187,9 @@ def test_batched_gate_generator_equals_per_head_loop(monkeypatch):
         gate2, _ = M.multihead_gate(mh, Q_all, None)
         per2 = torch.cat([M.head_gate(h, Q_all[:, :, i], None)[0] for i, h in enumerate(mh.heads)], 1)
     assert _crel(gate2.numpy(), per2.numpy()) < 1e-5 and _crel(gate2.numpy(), gate.numpy()) > 1e-3
+    # ... and writes through .data (EMA swaps, old-style optimizers: no version bump, same storage) are seen too
+    with torch.no_grad():
+        mh.heads[0].gate_mlp[2].bias.data.copy_(mh.heads[0].gate_mlp[2].bias.data + 2.0)
+        gate3, _ = M.multihead_gate(mh, Q_all, None)
+        per3 = torch.cat([M.head_gate(h, Q_all[:, :, i], None)[0] for i, h in enumerate(mh.heads)], 1)
+    assert _crel(gate3.numpy(), per3.numpy()) < 1e-5 and _crel(gate3.numpy(), gate2.numpy()) > 1e-3
