@@ -24,6 +24,7 @@ SYMBOLS = (
     "spectre_mix_fwd_anchors",
     "spectre_mix_anchors_workspace_bytes",
     "spectre_mix_workspace_bytes",
+    "spectre_mix_dgate",
     "spectre_mix_fwd_host",
     "spectre_rfft_fwd",
     "spectre_decode_update",
@@ -96,6 +97,8 @@ def load():
                                                 i32, i32, i32, i32, i32, vp, ctypes.c_size_t, vp]
         lib.spectre_mix_anchors_workspace_bytes.restype = ctypes.c_size_t
         lib.spectre_mix_anchors_workspace_bytes.argtypes = [i32, i32, i32, i32, i32, i32]
+        lib.spectre_mix_dgate.restype = i32
+        lib.spectre_mix_dgate.argtypes = [vp, vp, i32, i64, i64, i64, i64, vp, i32, i32, i32, i32, i32, vp]
         lib.spectre_mix_fwd_host.restype = i32
         lib.spectre_mix_fwd_host.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32]
         lib.spectre_rfft_fwd.restype = i32

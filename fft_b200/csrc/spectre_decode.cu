@@ -22,6 +22,19 @@ namespace {
 
 constexpr int kKChunk = 16;  // frequency bins per block
 
+// sin / cos of a float32 angle of any size the decode path produces (|theta| up to ~1e5 rad): two-constant Cody-Waite
+// reduction by 2 pi with fused multiply-adds (exact to ~1e-7 rad for |n| < 2^16), then the special-function unit on
+// [-pi, pi] (absolute error ~5e-7).  The ANGLE keeps the reference's float32 rounding order (that is what parity needs: at
+// 1e4 rad a float32 angle is only known to 1e-3 rad, and the reference uses exactly that value); its sine and cosine need
+// not be correctly rounded -- sincosf costs ~4x the instructions on the kernel's critical path.
+__device__ __forceinline__ void sincos_reduced(float theta, float *s, float *c) {
+    const float n = rintf(theta * 0.15915494309189535f);
+    float r = fmaf(n, -6.2831854820251465f, theta);      // 2 pi = 6.2831854820251465 - 1.7484555e-7
+    r = fmaf(n, 1.7484555e-7f, r);
+    *s = __sinf(r);
+    *c = __cosf(r);
+}
+
 // mode bit 0: update the spectrum; bit 1: read one output sample out
 template <int MODE>
 __global__ void __launch_bounds__(256) decode_kernel(float2 *__restrict__ prefix, const float *__restrict__ v_new,
@@ -43,6 +56,7 @@ __global__ void __launch_bounds__(256) decode_kernel(float2 *__restrict__ prefix
     const float posf = (float)pos, nf = (float)n_fft;
     const float nyq_sign = (pos & 1) ? -1.f : 1.f;
     float acc = 0.f;
+#pragma unroll 8
     for (int k = k0; k < k1; ++k) {
         float2 X = prefix[(size_t)k * d + c];
         const float kf = (float)k;
@@ -50,12 +64,12 @@ __global__ void __launch_bounds__(256) decode_kernel(float2 *__restrict__ prefix
             const float a = __fmul_rn(w32, kf);
             if (evict) {   // spectre.py:799-802: subtract the evicted token first
                 float s, co;
-                sincosf(__fmul_rn(a, t_old), &s, &co);
+                sincos_reduced(__fmul_rn(a, t_old), &s, &co);
                 X.x -= co * vo;
                 X.y -= s * vo;
             }
             float s, co;
-            sincosf(__fmul_rn(a, t_new), &s, &co);
+            sincos_reduced(__fmul_rn(a, t_new), &s, &co);
             X.x += co * vn;
             X.y += s * vn;
             prefix[(size_t)k * d + c] = X;
@@ -65,7 +79,7 @@ __global__ void __launch_bounds__(256) decode_kernel(float2 *__restrict__ prefix
             const float yr = g.x * X.x - g.y * X.y;           // gate_broadcast * prefix_fft
             const float yi = g.x * X.y + g.y * X.x;
             float s, co;
-            sincosf(__fdiv_rn(__fmul_rn(__fmul_rn(two_pi32, kf), posf), nf), &s, &co);
+            sincos_reduced(__fdiv_rn(__fmul_rn(__fmul_rn(two_pi32, kf), posf), nf), &s, &co);
             const float contrib = yr * co - yi * s;
             float wgt = 2.f;                                    // spectre.py:643-653
             if (k == 0) wgt = 1.f;

@@ -692,6 +692,65 @@ size_t spectre_mix_workspace_bytes(int v_dtype, int B, int N, int n_fft, int C, 
     return (size_t)two_pass_rows(B, n_fft, C) * (size_t)n_fft * C * sizeof(float);
 }
 
+int spectre_mix_dgate(const void *v, const void *dy, int dtype, int64_t v_stride_b, int64_t v_stride_n, int64_t dy_stride_b,
+                      int64_t dy_stride_n, void *dgate, int B, int N, int n_fft, int C, int group_width, void *stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    if (int rc = check_common(B, N, n_fft, C, group_width)) return rc;
+    if (dtype != SPECTRE_MIX_F32 && dtype != SPECTRE_MIX_BF16) return fail(SPECTRE_MIX_ERR_UNSUPPORTED, "dtype %d unsupported", dtype);
+    const int n_io = std::min(N, n_fft);
+    const int NG = C / group_width, F_half = n_fft / 2 + 1;
+    if (B == 0 || C == 0) return 0;
+    if (!dgate || ((!v || !dy) && n_io > 0)) return fail(SPECTRE_MIX_ERR_BAD_ARG, "null pointer (v=%p dy=%p dgate=%p)", v, dy, dgate);
+    if (!aligned(dgate, 8)) return fail(SPECTRE_MIX_ERR_UNSUPPORTED, "dgate must be 8-byte aligned");
+    DeviceState *st = nullptr;
+    if (int rc = get_device_state(&st, nullptr)) return rc;
+    // the fused variant: packed layout, TMEM-staged kernel of this n_fft, whole tiles inside one gate group
+    const KernelEntry *k = nullptr;
+    for (const KernelEntry &e : registry())
+        if (e.n_fft == n_fft && e.io == dtype && e.mode == spx::MODE_QUAD && !e.sub && e.launch_dgate && e.tmem_ok) { k = &e; break; }
+    const int tile_ch = k ? mode_channels(k->mode) * k->ncol : 0;
+    const int mode = pick_mode(dtype, group_width, v, v_stride_b, v_stride_n, dy, dy_stride_b, dy_stride_n, nullptr, 0);
+    if (!k || mode != spx::MODE_QUAD || group_width % tile_ch != 0 || !tma_layout_ok(v, dtype, v_stride_b, v_stride_n) ||
+        !tma_layout_ok(dy, dtype, dy_stride_b, dy_stride_n) || (int)k->smem_bytes(1, true, true) > st->max_smem_optin)
+        return fail(SPECTRE_MIX_ERR_UNSUPPORTED,
+                    "no fused gate-gradient kernel for n_fft=%d dtype=%d group_width=%d (built for n_fft = 4096, group widths that are "
+                    "multiples of 8, 16-byte aligned rows); use the two-spectrum formulation", n_fft, dtype, group_width);
+    const float2 *tw = nullptr;
+    if (int rc = get_twiddles(*st, *k, &tw)) return rc;
+    cudaError_t e = cudaMemsetAsync(dgate, 0, (size_t)B * NG * F_half * sizeof(float2), stream);   // tiles of a group add into it
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(dgate)");
+    if (n_io == 0) return 0;
+    MixParams p;
+    memset(&p, 0, sizeof(p));
+    p.v = v;
+    p.out = dgate;
+    p.tw = tw;
+    p.v_sb = v_stride_b;
+    p.v_sn = v_stride_n;
+    p.B = B;
+    p.n_in = n_io;
+    p.n_out = n_io;
+    p.C = C;
+    p.group_width = group_width;
+    p.NG = NG;
+    p.tiles_per_row = (C / 4 + k->ncol - 1) / k->ncol;
+    p.num_tiles = B * p.tiles_per_row;
+    p.gate_tables = 1;
+    p.inv_n = 1.0f / (float)n_fft;
+    p.skew_ns = g_skew_ns.load(std::memory_order_relaxed);
+    p.sched = g_sched.load(std::memory_order_relaxed) & ~(16 | 8 | 4);
+    p.sub_R = 1;
+    p.gw_shift = ilog2_exact(group_width);
+    alignas(64) CUtensorMap tmap_v, tmap_dy;
+    if (!make_v_tensor_map(&tmap_v, v, dtype, v_stride_b, v_stride_n, B, n_io, C, spx::kTmaBoxRows, tile_ch, 0) ||
+        !make_v_tensor_map(&tmap_dy, dy, dtype, dy_stride_b, dy_stride_n, B, n_io, C, spx::kTmaBoxRows, tile_ch, 0))
+        return fail(SPECTRE_MIX_ERR_UNSUPPORTED, "cuTensorMapEncodeTiled failed for V / dY");
+    const int grid = std::min(p.num_tiles, st->sm_count);
+    e = k->launch_dgate(p, grid, &tmap_v, &tmap_dy, stream);
+    if (e != cudaSuccess) return cuda_fail(e, "gate-gradient kernel launch");
+    return 0;
+}
+
 int spectre_mix_plan(int v_dtype, int out_dtype, int has_mem, int B, int N, int n_fft, int C, int group_width,
                      spectre_mix_plan_info *info) {
     if (!info) return fail(SPECTRE_MIX_ERR_BAD_ARG, "info is null");

@@ -1,4 +1,5 @@
-// generated by gen_instances.py -- kernel variants for n_fft group "small"
+// Kernel variants for n_fft group "small": one table per file so that the instantiations compile in parallel (make -j).
+// Registry order matters: the first entry of a (n_fft, dtype, mode) that fits is the default (spectre_mix_api.cu: choose()).
 #include "spectre_mix_registry.h"
 #include "../../include/spectre_mix.h"
 

@@ -790,7 +790,7 @@ __device__ __forceinline__ void gate_put_sub(float2 *gs, const float2 (&gv)[GKS]
 // spectrum.  TMA_IN: the tile is brought into shared memory by TMA (cp.async.bulk.tensor) and the CTA's next
 // tile is prefetched into L2 by the TMA unit; otherwise stage 0 loads straight from global into registers.
 template <class PL, int MODE, int NCOL, int NT, int MINB, class TIN, class TOUT, bool HAS_MEM, bool RFFT_ONLY = false,
-          bool TMA_IN = false, bool TMEM_IO = false, bool ANCH = false>
+          bool TMA_IN = false, bool TMEM_IO = false, bool ANCH = false, bool DGATE = false>
 __global__ void __launch_bounds__(NT + ((TMA_IN && NT >= kSepProducerMinThreads) ? kProducerThreads : 0), MINB)
     spectre_mix_kernel(const MixParams p, const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_out) {
     using E = Elem<MODE>;
@@ -805,6 +805,12 @@ __global__ void __launch_bounds__(NT + ((TMA_IN && NT >= kSepProducerMinThreads)
     constexpr int ITERS0 = (ITEMS0 + NT - 1) / NT;          // per thread
     static_assert(!TMA_IN || (MODE == MODE_QUAD && !RFFT_ONLY), "TMA path is built for the packed mix kernel");
     static_assert(!ANCH || (!RFFT_ONLY && !SPX_GATE_ASYNC), "in-kernel gate generation: mix kernels, register-staged gate rows");
+    // DGATE (backward of the mix w.r.t. the gate): every tile is visited twice -- first with V's rows (forward
+    // transform, packed spectrum stashed in this thread's own tensor-memory lane: the TMEM-OUT half is free, nothing is
+    // drained), then with dY's rows (tensor map 2), whose spectrum is multiplied by the conjugate of the stash, reduced over the
+    // channels of the gate group and over the mirrored bin, and added to dgate[b, g, :].  No inverse passes, no gate, no output tile.
+    static_assert(!DGATE || (TMEM_IO && !RFFT_ONLY && !ANCH && !HAS_MEM && !PL::kSub && MODE == MODE_QUAD && PL::NS == 3),
+                  "dgate kernel: TMEM-staged packed variant of a three-stage plan");
     // stage NS-2 and the middle pass both have radix 16 and >= 32 butterflies per column, items map to threads
     // identically in both (w = tid + k NT): their exchange stays inside a warp
     constexpr bool kWarpLocal = (NS >= 3) && (PL::R(NS - 1) == 16) && (PL::R(NS - 2) == 16) && (NT % 32 == 0) &&
@@ -953,13 +959,14 @@ __global__ void __launch_bounds__(NT + ((TMA_IN && NT >= kSepProducerMinThreads)
             // therefore stay in flight while results drain (DEPTH boxes ahead), and the load stream runs across tile
             // boundaries.  Load box idx (stream index over all tiles of this CTA) is consumed at step idx, in slot idx % slots.
             // tile sequence of this CTA: tile_of(s), s = 0, 1, ...; paired: tiles 2P, 2P+1 of pair P = blockIdx.x + (s / 2) gridDim.x
-            const bool pair = p.pair_tiles != 0;
+            const bool pair = !DGATE && p.pair_tiles != 0;
             auto tile_of = [&](int s_) {
+                if constexpr (DGATE) return (int)blockIdx.x + (s_ >> 1) * (int)gridDim.x;      // every tile twice: V rows, then dY rows
                 return pair ? 2 * ((int)blockIdx.x + (s_ >> 1) * (int)gridDim.x) + (s_ & 1) : (int)blockIdx.x + s_ * (int)gridDim.x;
             };
             const int units = pair ? p.num_tiles / 2 : p.num_tiles;     // pairs or tiles dealt round robin to the CTAs
             const int my_units = ((int)blockIdx.x < units && !idle) ? (units - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
-            const int my_tiles = pair ? 2 * my_units : my_units;
+            const int my_tiles = (pair || DGATE) ? 2 * my_units : my_units;
             const int total_boxes = my_tiles * NBOX;
             // load stream state (used by the elected thread): next box to issue, kept incrementally -- the elected thread's
             // path between two barriers is the helper's critical path, so no divisions there except once per tile
@@ -973,7 +980,8 @@ __global__ void __launch_bounds__(NT + ((TMA_IN && NT >= kSepProducerMinThreads)
                 // (no proxy fence: the slot was last touched by shared-memory READS of the helper threads, ordered by the
                 // helper barrier, or by a TMA store whose read the store thread has waited for)
                 mbar_expect_tx(bar_landed + 8 * ld_slot, SLOTB);
-                tma_load_3d(smem_u32(stg) + ld_slot * SLOTB, &tmap, ld_tc, ld_k * kTmaBoxRows, ld_tb, bar_landed + 8 * ld_slot);
+                tma_load_3d(smem_u32(stg) + ld_slot * SLOTB, (DGATE && (ld_seq & 1)) ? &tmap_out : &tmap, ld_tc, ld_k * kTmaBoxRows, ld_tb,
+                            bar_landed + 8 * ld_slot);
                 --ld_left;
                 ld_slot = (ld_slot + 1 == kTmemSlots) ? 0 : ld_slot + 1;
                 if (++ld_k == NBOX) {
@@ -1002,10 +1010,10 @@ __global__ void __launch_bounds__(NT + ((TMA_IN && NT >= kSepProducerMinThreads)
                                  (sizeof(TIN) == 4) && (p.n_in == N) && hl < 64;
 #endif
             uint32_t sl = 0, landed_par = 0;                      // ring slot of the current step; one landed-parity bit per slot
-            const int phases = my_tiles > 0 ? my_tiles + 2 : 0;
+            const int phases = my_tiles > 0 ? my_tiles + (DGATE ? 0 : 2) : 0;
 #pragma unroll 1
             for (int P = 0; P < phases; ++P) {
-                const bool do_park = P < my_tiles, do_drain = P >= 2;
+                const bool do_park = P < my_tiles, do_drain = !DGATE && P >= 2;
 #if SPX_HELPER_TL
                 // diagnostic build: the elected thread records, per phase, entry / start / end stamps (ns) and the cycles it
                 // spent waiting for landings, moving data, at the helper barrier and in its TMA duties
@@ -1158,7 +1166,7 @@ __global__ void __launch_bounds__(NT + ((TMA_IN && NT >= kSepProducerMinThreads)
     // warp's serial path between two tiles, so the loop has none (group index by shift when group_width is a power of two)
     // Paired order (TMEM variant, p.pair_tiles): tiles 2P and 2P+1 of pair P = blockIdx.x + k gridDim.x back to back -- the two
     // channel tiles of one gate group, so the gate row is staged (or, ANCH, generated) once per pair.
-    const bool pair = TMEM_IO && p.pair_tiles != 0;
+    const bool pair = TMEM_IO && !DGATE && p.pair_tiles != 0;
     const int stride = pair ? 2 * (int)gridDim.x : (int)gridDim.x;
     const int step_row = stride / p.tiles_per_row, step_col = stride - step_row * p.tiles_per_row;
     const int first_tile = pair ? 2 * (int)blockIdx.x : (int)blockIdx.x;
@@ -1167,7 +1175,11 @@ __global__ void __launch_bounds__(NT + ((TMA_IN && NT >= kSepProducerMinThreads)
     auto gdiv = [&](int x) { return p.gw_shift >= 0 ? (x >> p.gw_shift) : x / p.group_width; };
     for (int tile = first_tile; tile < p.num_tiles; tile = tile_next_, brow = nrow_, tcol = ncol_, ++seq) {
         const bool partner_next = pair && !(seq & 1);   // the next tile is the second half of this pair: same row, same gate row
-        if (partner_next) {
+        if (DGATE && !(seq & 1)) {                      // dgate: the same tile again, with dY's rows
+            nrow_ = brow;
+            ncol_ = tcol;
+            tile_next_ = tile;
+        } else if (partner_next) {
             nrow_ = brow;
             ncol_ = tcol + 1;
             tile_next_ = tile + 1;
@@ -1187,7 +1199,7 @@ __global__ void __launch_bounds__(NT + ((TMA_IN && NT >= kSepProducerMinThreads)
 
         // ---- stage the gate tables of this tile (asynchronous copies, awaited before the barrier that follows stage 0).
         // With one table per tile this was already started while the previous tile finished (see below); else do it here.
-        if constexpr (!RFFT_ONLY) {
+        if constexpr (!RFFT_ONLY && !DGATE) {
             if constexpr (SUB) {
                 if (seq == 0) {
                     float2 gv[GKS];
@@ -1297,7 +1309,7 @@ __global__ void __launch_bounds__(NT + ((TMA_IN && NT >= kSepProducerMinThreads)
                 if (ITEMS0 % NT == 0 || w < ITEMS0) {
                     Dft<R0, V>::run(x0[it]);
                     apply_twiddles<PL, 0, V>(x0[it], tw, p.tw, u);
-                    if constexpr (TMEM_IO) {
+                    if constexpr (TMEM_IO && !DGATE) {
                         // split barrier: every warp has pulled the previous tile's last pass out of the buffer
                         if ((p.sched & 2) && tile_it >= 1) mbar_wait(bar + 112, (tile_it - 1) & 1);
                     }
@@ -1351,6 +1363,41 @@ __global__ void __launch_bounds__(NT + ((TMA_IN && NT >= kSepProducerMinThreads)
                     }
                     continue;
                 }
+                if constexpr (DGATE) {
+                    // this thread's private stash: its own tensor-memory lane, 64 columns of the (otherwise unused) TMEM-OUT half
+                    const uint32_t ts = tmem_base + ((uint32_t)(32 * ((tid >> 5) & 3)) << 16) + (uint32_t)(TCOLS + 64 * (tid >> 7));
+                    if (!(seq & 1)) {
+                        // V's rows: keep the packed spectrum Z[k], k = klow + PLAST q, until dY's spectrum of the same tile is here
+#pragma unroll
+                        for (int q = 0; q < RL; ++q) tmem_st4(ts + 4 * q, x[q].re.x, x[q].re.y, x[q].im.x, x[q].im.y);
+                        tmem_wait_st();
+                    } else {
+                        // dY's rows: T[k] = sum over the two packed lanes of conj(Z[k]) W[k]  (Z = v_a + i v_b, W = d_a + i d_b; the
+                        // per-channel products conj(V_c) D_c are recovered below from T[k] + conj(T[N - k]))
+                        float2 t[RL];
+#pragma unroll
+                        for (int q = 0; q < RL; ++q) {
+                            Cx<V> z;
+                            tmem_ld4(ts + 4 * q, z.re.x, z.re.y, z.im.x, z.im.y);
+                            tmem_wait_ld();
+                            const float2 re2 = __ffma2_rn(z.im, x[q].im, __fmul2_rn(z.re, x[q].re));                     // Zre Wre + Zim Wim
+                            const float2 im2 = __ffma2_rn(make_float2(-z.im.x, -z.im.y), x[q].re, __fmul2_rn(z.re, x[q].im));   // Zre Wim - Zim Wre
+                            t[q] = make_float2(re2.x + re2.y, im2.x + im2.y);
+                        }
+                        // (one item per thread and full tiles in this variant -- the host checks C % tile channels == 0 -- so every
+                        // thread of the CTA reaches this barrier exactly once)
+                        cta_sync<NT, SEP>();                 // every warp has pulled its middle-pass inputs out of the buffer
+                        // T in natural bin order, padded like the gate table (k + (k >> 4)): conflict-free to write (lanes 16 bins
+                        // apart) and to read (consecutive bins)
+                        float2 *tn = reinterpret_cast<float2 *>(buf) + (size_t)col * (N + (N >> 4) + 1);
+#pragma unroll
+                        for (int q = 0; q < RL; ++q) {
+                            const int k = klow + PLAST * q;
+                            tn[k + (k >> 4)] = t[q];
+                        }
+                    }
+                    continue;
+                }
                 const float2 *gs = gate_s + (p.gate_tables == 1 ? 0 : (gdiv(cabs) - g0) * GS);
                 // bins k = klow + PLAST q (q < RL/2) use G[k]; the mirrored half uses conj(G[N - k])
                 const int plo = klow + (klow >> 4);                // padded index of bin klow
@@ -1394,6 +1441,35 @@ __global__ void __launch_bounds__(NT + ((TMA_IN && NT >= kSepProducerMinThreads)
 #pragma unroll
                 for (int m = 0; m < RL; ++m) cb[m] = E::pack(cswap(x[m]));
             }
+        }
+        if constexpr (DGATE) {
+            if (seq & 1) {
+                cta_sync<NT, SEP>();                         // T of both element columns is in the buffer
+                // dgate[b, g, k] += w_k / (2 n) * sum over columns of (T[k] + conj(T[(N - k) mod N])), k <= N/2, fixed order;
+                // imag(DC) = imag(Nyquist) = 0 (irfft ignores them, so their gradient is zero)
+                const float2 *tn = reinterpret_cast<const float2 *>(buf);
+                float2 *dg = reinterpret_cast<float2 *>(p.out) + ((long long)b * p.NG + g0) * (N / 2 + 1);
+                constexpr int TS = N + (N >> 4) + 1;
+                for (int k = tid; k <= N / 2; k += NT) {
+                    const int km = (N - k) & (N - 1);
+                    float sr = 0.f, si = 0.f;
+#pragma unroll
+                    for (int c = 0; c < NCOL; ++c) {
+                        if ((ce0 + c) >= CE) continue;
+                        const float2 a = tn[(size_t)c * TS + k + (k >> 4)], m = tn[(size_t)c * TS + km + (km >> 4)];
+                        sr += a.x + m.x;
+                        si += a.y - m.y;
+                    }
+                    const bool edge = (k == 0) || (k == N / 2);
+                    const float sc = (edge ? 0.5f : 1.0f) * p.inv_n;
+                    atomicAdd(&dg[k].x, sr * sc);
+                    if (!edge) atomicAdd(&dg[k].y, si * sc);
+                }
+            }
+            cta_sync<NT, SEP>();                             // the next visit's stage 0 rewrites the buffer
+            ++tl_tile;
+            ++tile_it;
+            continue;
         }
         if constexpr (kWarpLocal && !RFFT_ONLY) __syncwarp(); else cta_sync<NT, SEP>();
         SPX_MARK(4)

@@ -30,6 +30,8 @@ struct KernelEntry {
     int anch_ok;   // 1: variants that evaluate the gate from anchors inside the gate staging exist (packed mode)
     // forward half only (half spectrum out); MODE_REAL variants only, else nullptr
     cudaError_t (*launch_rfft)(const MixParams &p, int grid, cudaStream_t st);
+    // gate gradient: TMEM-staged packed variants only, else nullptr; tmap_v / tmap_dy describe V and dY
+    cudaError_t (*launch_dgate)(const MixParams &p, int grid, const CUtensorMap *tmap_v, const CUtensorMap *tmap_dy, cudaStream_t st);
 };
 
 template <class PL, int MODE, int NCOL, int NT, int MINB, class TIO>
@@ -87,6 +89,22 @@ struct Launcher {
         void *args[] = {&pc, &tm, &tmo};
         return cudaLaunchKernel(f, dim3(grid), dim3(NT), args, sm, st);
     }
+    static cudaError_t launch_dgate(const MixParams &p, int grid, const CUtensorMap *tmap_v, const CUtensorMap *tmap_dy, cudaStream_t st) {
+        if constexpr (kTmem && PL::NS == 3 && !PL::kSub) {
+            const size_t sm = smem_bytes(1, true, true);
+            const void *f = reinterpret_cast<const void *>(
+                &spectre_mix_kernel<PL, MODE, NCOL, NT, MINB, TIO, TIO, false, false, true, true, false, true>);
+            cudaError_t e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+            if (e != cudaSuccess) return e;
+            MixParams pc = p;
+            alignas(64) CUtensorMap tm = *tmap_v, tmo = *tmap_dy;
+            void *args[] = {&pc, &tm, &tmo};
+            return cudaLaunchKernel(f, dim3(grid), dim3(NT + kProducerThreads), args, sm, st);
+        } else {
+            return cudaErrorNotSupported;
+        }
+    }
+    static constexpr bool kDgate = kTmem && PL::NS == 3 && !PL::kSub;
     static int occupancy(int gate_tables, bool has_mem, bool tma, bool tmem) {
         const size_t sm = smem_bytes(gate_tables, tma, tmem);
         const void *f = pick(has_mem, tma, tmem);
@@ -125,7 +143,9 @@ struct RfftPtr<PL, MODE_REAL, NCOL, NT, MINB, TIO> {
             ::spx::Launcher<::spx::Plan<R0, R1, R2, R3>, MODE, NCOL, NT, MINB, TIO>::kTma ? 1 : 0,            \
             ::spx::Launcher<::spx::Plan<R0, R1, R2, R3>, MODE, NCOL, NT, MINB, TIO>::kTmem ? 1 : 0, 0,        \
             ::spx::Launcher<::spx::Plan<R0, R1, R2, R3>, MODE, NCOL, NT, MINB, TIO>::kAnch ? 1 : 0,           \
-            ::spx::RfftPtr<::spx::Plan<R0, R1, R2, R3>, MODE, NCOL, NT, MINB, TIO>::get()                     \
+            ::spx::RfftPtr<::spx::Plan<R0, R1, R2, R3>, MODE, NCOL, NT, MINB, TIO>::get(),                    \
+            ::spx::Launcher<::spx::Plan<R0, R1, R2, R3>, MODE, NCOL, NT, MINB, TIO>::kDgate                   \
+                ? &::spx::Launcher<::spx::Plan<R0, R1, R2, R3>, MODE, NCOL, NT, MINB, TIO>::launch_dgate : nullptr \
     }
 
 #define SPX_ENTRY_SUB(R0, R1, R2, R3, MODE, NCOL, NT, MINB, TIO, IOCODE)                                     \
@@ -139,7 +159,7 @@ struct RfftPtr<PL, MODE_REAL, NCOL, NT, MINB, TIO> {
             ::spx::Launcher<::spx::Plan<R0, R1, R2, R3, true>, MODE, NCOL, NT, MINB, TIO>::kTma ? 1 : 0,      \
             ::spx::Launcher<::spx::Plan<R0, R1, R2, R3, true>, MODE, NCOL, NT, MINB, TIO>::kTmem ? 1 : 0, 1,  \
             ::spx::Launcher<::spx::Plan<R0, R1, R2, R3, true>, MODE, NCOL, NT, MINB, TIO>::kAnch ? 1 : 0,     \
-            nullptr                                                                                           \
+            nullptr, nullptr                                                                                           \
     }
 
 // one table per instantiation file

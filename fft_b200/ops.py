@@ -113,28 +113,53 @@ def _mix_backward(ctx, dY):
         dV = full[:, :N]
         if N > n_fft:  # rows beyond n_fft never reached the transform (spectre.py:506 truncates)
             dV = torch.nn.functional.pad(dV, (0, 0, 0, N - n_fft))
-    if ctx.needs_input_grad[1] or (ctx.has_memory and ctx.needs_input_grad[2]):
-        dYf = rfft_seq(dY, n_fft)                                    # (B, F, C)
+    need_dmem = ctx.has_memory and ctx.needs_input_grad[2]
+    if ctx.needs_input_grad[1] or need_dmem:
         F_half = n_fft // 2 + 1
         w = torch.full((F_half,), 2.0 / n_fft, device=dY.device)
         w[0] = 1.0 / n_fft
         if n_fft % 2 == 0:
             w[-1] = 1.0 / n_fft
-        dYf = dYf * w[None, :, None]
         edge = torch.zeros(F_half, dtype=torch.bool, device=dY.device)
         edge[0] = True
         if n_fft % 2 == 0:
             edge[-1] = True
-        if ctx.has_memory and ctx.needs_input_grad[2]:
-            dmem = dYf.sum(0)
+        if need_dmem:
+            # the transform is linear: the batch sum of the spectra is the spectrum of the batch sum (one small transform)
+            dmem = rfft_seq(dY.float().sum(0, keepdim=True), n_fft)[0] * w[:, None]
             dmem = torch.where(edge[:, None], torch.complex(dmem.real, torch.zeros_like(dmem.real)), dmem)
         if ctx.needs_input_grad[1]:
-            Vf = rfft_seq(V, n_fft)
-            B, _, C = Vf.shape
-            prod = (torch.conj(Vf) * dYf).view(B, F_half, C // dg, dg).sum(-1)   # (B, F, NG)
-            prod = torch.where(edge[None, :, None], torch.complex(prod.real, torch.zeros_like(prod.real)), prod)
-            dgate = prod.permute(0, 2, 1).contiguous()
+            dgate = _dgate_fused(V, dY, n_fft, dg)
+            if dgate is None:   # layouts without the fused kernel: two half spectra + stock reductions
+                dYf = rfft_seq(dY, n_fft) * w[None, :, None]
+                Vf = rfft_seq(V, n_fft)
+                B, _, C = Vf.shape
+                prod = (torch.conj(Vf) * dYf).view(B, F_half, C // dg, dg).sum(-1)   # (B, F, NG)
+                prod = torch.where(edge[None, :, None], torch.complex(prod.real, torch.zeros_like(prod.real)), prod)
+                dgate = prod.permute(0, 2, 1).contiguous()
     return dV, dgate, dmem, None, None
+
+
+def _dgate_fused(V: torch.Tensor, dY: torch.Tensor, n_fft: int, group_width: int):
+    """``spectre_mix_dgate``: the gate gradient in ONE kernel (both forward transforms, the per-group reduction of
+    ``conj(V_fft) * dY_fft`` on chip; no spectrum reaches HBM).  Returns None where no fused variant exists."""
+    if V.dtype not in _DT:
+        return None
+    V = _rows_last_contig(V)
+    dY = _rows_last_contig(dY.to(V.dtype))
+    B, N, C = V.shape
+    dgate = torch.empty((B, C // group_width, n_fft // 2 + 1), dtype=torch.complex64, device=V.device)
+    if dgate.numel() == 0:
+        return dgate
+    lib = _lib.load()
+    with torch.cuda.device(V.device):
+        stream = torch.cuda.current_stream(V.device).cuda_stream
+        rc = lib.spectre_mix_dgate(V.data_ptr(), dY.data_ptr(), _DT[V.dtype], V.stride(0), V.stride(1), dY.stride(0), dY.stride(1),
+                                   dgate.data_ptr(), B, N, n_fft, C, group_width, ctypes.c_void_p(stream))
+    if rc == 2:          # SPECTRE_MIX_ERR_UNSUPPORTED: no fused variant for this layout
+        return None
+    _lib.check(rc, "spectral_mix dgate")
+    return dgate
 
 
 _spectral_mix_op.register_autograd(_mix_backward, setup_context=_mix_setup_context)

@@ -103,6 +103,20 @@ int spectre_mix_fwd_anchors(const void *v, int v_dtype, int64_t v_stride_b, int6
                             int B, int N, int n_fft, int C, int group_width,
                             void *workspace, size_t workspace_bytes, void *stream);
 
+/* Gradient of the mix with respect to the gate (autograd through spectre.py:506-553), for dY = d loss / d out:
+ *   dgate[b, g, k] = w_k / n_fft * sum over the group's channels c of conj(rfft(V[b,:,c]))[k] * rfft(dY[b,:,c])[k]
+ * (w = 1 at bin 0 and n_fft/2, 2 elsewhere; imaginary parts at those two bins are zero, as irfft ignores them).  ONE kernel:
+ * V's tile is transformed and its packed spectrum parked in tensor memory, dY's tile of the same channels follows, the
+ * products are reduced over channel pairs, the mirrored bin and the gate group on chip -- neither spectrum reaches HBM.
+ *   v, dy   device, [B][N][C] (dy: [B][min(N,n_fft)][C] is fine, rows beyond are zero), same dtype, strides in elements
+ *   dgate   device, complex64 [B][C/group_width][n_fft/2+1] contiguous (overwritten)
+ * Built for n_fft = 4096, group widths that are multiples of 8 and 16-byte aligned rows; returns SPECTRE_MIX_ERR_UNSUPPORTED
+ * otherwise (the binding then forms the two spectra with spectre_rfft_fwd).  The gradient with respect to V needs no entry
+ * of its own: dV = spectre_mix_fwd(dY, conj(gate)). */
+int spectre_mix_dgate(const void *v, const void *dy, int dtype, int64_t v_stride_b, int64_t v_stride_n,
+                      int64_t dy_stride_b, int64_t dy_stride_n, void *dgate,
+                      int B, int N, int n_fft, int C, int group_width, void *stream);
+
 /* Same function on HOST buffers (what a non-CUDA host language binds): copies
  * v/gate/mem to the device in batch chunks, runs the kernel and copies the
  * result back, overlapping the three on internal streams; returns when `out`

@@ -417,6 +417,44 @@ def test_autograd_matches_oracle(fb, oracle, dev):
         assert rel_l2(torch.view_as_real(mg.grad).cpu().numpy(), torch.view_as_real(mc.grad).numpy()) < 1e-5
 
 
+def test_autograd_at_metric_shape_fused_gate_gradient(fb, oracle, dev):
+    """Backward at the metric shape (2, 4096, 768), 48 gate groups: dV through the mix kernel, dgate through the fused
+    gate-gradient kernel (spectre_mix_dgate: both transforms and the group reduction in one launch), dmemory by linearity;
+    against autograd through the oracle's torch.fft path.  Also ragged N, group widths 8 / 24 and bf16 inputs."""
+    import ctypes
+    from fft_b200 import _lib, ops
+    lib = _lib.load()
+    for (B, N, n_fft, C, dg, dt) in [(2, 4096, 4096, 768, 16, torch.float32), (2, 3000, 4096, 48, 8, torch.float32),
+                                     (1, 4096, 4096, 48, 24, torch.float32), (2, 4096, 4096, 64, 16, torch.bfloat16)]:
+        V, gate, mem = _rand_case(B, N, n_fft, C, dg, True, seed=300 + C + N)
+        if dt == torch.bfloat16:
+            V = V.to(dt).float()
+        w = torch.randn(B, min(N, n_fft), C, generator=torch.Generator().manual_seed(2))
+        Vc, gc, mc = V.clone().requires_grad_(), gate.clone().requires_grad_(), mem.clone().requires_grad_()
+        (oracle.mix_flat(Vc, gc, n_fft, dg, mc) * w).sum().backward()
+        # the fused kernel is the one that runs here
+        dg_direct = ops._dgate_fused(V.to(dev).to(dt), w.to(dev).to(dt), n_fft, dg)
+        assert dg_direct is not None, "fused gate-gradient kernel not used at n_fft = 4096"
+        tol = 1e-5 if dt == torch.float32 else 1e-2
+        assert rel_l2(torch.view_as_real(dg_direct).cpu().numpy(), torch.view_as_real(gc.grad).numpy()) < tol
+        if dt == torch.float32:
+            Vg, gg, mg = (V.to(dev).requires_grad_(), gate.to(dev).requires_grad_(), mem.to(dev).requires_grad_())
+            (fb.spectral_mix(Vg, gg, mg, n_fft=n_fft, group_width=dg) * w.to(dev)).sum().backward()
+            assert rel_l2(Vg.grad.cpu().numpy(), Vc.grad.numpy()) < 1e-5
+            assert rel_l2(torch.view_as_real(gg.grad).cpu().numpy(), torch.view_as_real(gc.grad).numpy()) < 1e-5
+            assert rel_l2(torch.view_as_real(mg.grad).cpu().numpy(), torch.view_as_real(mc.grad).numpy()) < 1e-5
+    # imaginary parts at DC / Nyquist are exactly zero, and the call is repeatable bit for bit at group width 16 (two tiles per group)
+    a = ops._dgate_fused(V.to(dev).to(dt), w.to(dev).to(dt), n_fft, dg)
+    b = ops._dgate_fused(V.to(dev).to(dt), w.to(dev).to(dt), n_fft, dg)
+    assert torch.equal(a, b) and float(a.imag[:, :, 0].abs().max()) == 0.0 and float(a.imag[:, :, -1].abs().max()) == 0.0
+    # sizes without a fused variant report UNSUPPORTED (the binding then takes the two-spectrum route, tested above at 128 / 1024)
+    x = torch.randn(1, 1024, 16, device=dev)
+    out = torch.empty(1, 1, 513, dtype=torch.complex64, device=dev)
+    rc = lib.spectre_mix_dgate(x.data_ptr(), x.data_ptr(), 0, x.stride(0), x.stride(1), x.stride(0), x.stride(1), out.data_ptr(),
+                               1, 1024, 1024, 16, 16, ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+    assert rc == 2 and b"no fused gate-gradient kernel" in lib.spectre_mix_last_error()
+
+
 # --------------------------------------------------------------------------- drop-in module shells
 @pytest.mark.parametrize("name", ["block_d64_h4_n128_mem", "block_d64_h4_n128"])
 def test_block_shell_matches_reference_block(name, fb, dev):
