@@ -96,7 +96,7 @@ struct DeviceState {
     cudaError_t init_err = cudaSuccess;
     int sm_count = 0;
     int max_smem_optin = 0;
-    std::atomic<float2 *> twiddles[kMaxLog2N + 1] = {};   // log2(n_fft) -> device table (plain and SUB plans of one n_fft share it)
+    std::atomic<float2 *> twiddles[2 * (kMaxLog2N + 1)] = {};   // (log2(n_fft), radix order) -> device table (plain and SUB plans share it)
     std::mutex mu;                                        // table creation, occupancy cache, pool creation
     std::map<std::pair<const KernelEntry *, int>, int> occupancy;  // (entry, flags) -> CTAs/SM
     // Scratch of the two-pass long-context path when the caller passes no workspace: stream-ordered allocations
@@ -162,6 +162,7 @@ int get_device_state(DeviceState **out, int *dev_out) {
 int get_twiddles(DeviceState &st, const KernelEntry &k, const float2 **tw) {
     int lg = 0;
     while ((1 << lg) < k.n_fft) ++lg;
+    if (k.radix[0] == 16 && k.radix[1] == 2) lg += kMaxLog2N + 1;   // the radix-16-first order of n_fft = 8192 has its own table
     float2 *d = st.twiddles[lg].load(std::memory_order_acquire);
     if (!d) {
         // first use of this n_fft on this device: build in double on the host, upload (synchronous -- do one warm-up call
@@ -419,9 +420,21 @@ int two_pass_rows(int B, int n_fft, int C) {
 }
 
 // does this call take the two-pass long-context path?  (QUAD layout, group width a multiple of 8, n_fft > 4096)
-const KernelEntry *two_pass_kernel(int n_fft, int mode, int group_width, const void *mem, long long mem_stride) {
-    if (!g_use_two_pass.load(std::memory_order_relaxed) || n_fft <= 4096 || mode != spx::MODE_QUAD || group_width % 8 != 0) return nullptr;
+// g_use_two_pass: 0 never, 1 automatic (default: only where no TMEM-staged single-kernel variant of this n_fft exists -- the
+// single pass over HBM wins: 2600 against 1640 GB/s at n_fft = 8192, profiles/r02f_8192_single_kernel.txt), 2 wherever possible
+const KernelEntry *two_pass_kernel(int n_fft, int dtype, int mode, int group_width, const void *mem, long long mem_stride) {
+    const int knob = g_use_two_pass.load(std::memory_order_relaxed);
+    if (!knob || n_fft <= 4096 || mode != spx::MODE_QUAD || group_width % 8 != 0) return nullptr;
     if (mem && (mem_stride % 2 != 0)) return nullptr;
+    if (knob == 1 && g_use_tma.load(std::memory_order_relaxed) && g_use_tmem.load(std::memory_order_relaxed) &&
+        !g_tile_channels_override.load(std::memory_order_relaxed)) {
+        // the packed layout is 16-byte aligned by construction, so a TMEM-staged variant can always take it
+        for (const KernelEntry &k : registry())
+            if (k.n_fft == n_fft && k.io == dtype && k.mode == spx::MODE_QUAD && !k.sub) {
+                if (k.tmem_ok && group_width % (4 * k.ncol) == 0) return nullptr;   // the default (first) packed variant is TMEM-staged
+                break;
+            }
+    }
     return find_sub_kernel();
 }
 
@@ -477,7 +490,7 @@ int spectre_mix_set_timeline(void *device_buffer) {
 }
 
 int spectre_mix_set_two_pass(int enable) {
-    g_use_two_pass.store(enable ? 1 : 0);
+    g_use_two_pass.store(enable < 0 ? 0 : (enable > 2 ? 2 : enable));
     return 0;
 }
 
@@ -538,7 +551,7 @@ int mix_fwd_impl(const void *v, int v_dtype, int64_t v_stride_b, int64_t v_strid
 
     const int mode = pick_mode(v_dtype, group_width, v, v_stride_b, v_stride_n, out, out_stride_b, out_stride_n, mem,
                                mem_stride);
-    const KernelEntry *ks = two_pass_kernel(n_fft, mode, group_width, mem, mem_stride);
+    const KernelEntry *ks = two_pass_kernel(n_fft, v_dtype, mode, group_width, mem, mem_stride);
     Choice c;
     if (!ks) {
         if (int rc = choose(*st, n_fft, v_dtype, mode, C, group_width, &c)) return rc;
@@ -682,13 +695,12 @@ size_t spectre_mix_anchors_workspace_bytes(int v_dtype, int B, int N, int n_fft,
 }
 
 size_t spectre_mix_workspace_bytes(int v_dtype, int B, int N, int n_fft, int C, int group_width) {
-    (void)v_dtype;
     if (check_common(B, N, n_fft, C, group_width)) return 0;
     if (B == 0 || C == 0 || std::min(N, n_fft) == 0) return 0;
     // upper bound over layouts: the two-pass path is taken when the tensors allow the packed (QUAD) layout; a call that
     // falls back to a single-kernel variant ignores the workspace
     const int mode = (group_width % 4 == 0) ? spx::MODE_QUAD : ((group_width % 2 == 0) ? spx::MODE_PAIR : spx::MODE_REAL);
-    if (!two_pass_kernel(n_fft, mode, group_width, nullptr, 0)) return 0;
+    if (!two_pass_kernel(n_fft, v_dtype, mode, group_width, nullptr, 0)) return 0;
     return (size_t)two_pass_rows(B, n_fft, C) * (size_t)n_fft * C * sizeof(float);
 }
 
@@ -759,7 +771,7 @@ int spectre_mix_plan(int v_dtype, int out_dtype, int has_mem, int B, int N, int 
     DeviceState *st = nullptr;
     if (int rc = get_device_state(&st, nullptr)) return rc;
     const int mode = (group_width % 4 == 0) ? spx::MODE_QUAD : ((group_width % 2 == 0) ? spx::MODE_PAIR : spx::MODE_REAL);
-    const KernelEntry *ks = two_pass_kernel(n_fft, mode, group_width, nullptr, 0);
+    const KernelEntry *ks = two_pass_kernel(n_fft, v_dtype, mode, group_width, nullptr, 0);
     const bool g_use_tma = ::g_use_tma.load(std::memory_order_relaxed) != 0, g_use_tmem = ::g_use_tmem.load(std::memory_order_relaxed) != 0;
     Choice c;
     if (ks) {

@@ -6,6 +6,9 @@
 namespace spx {
 namespace {
 const KernelEntry kTable[] = {
+    // single-kernel TMEM-staged variant: radix-16 first (512 stage-0 butterflies = one per thread, rows u + 512 m in one tensor-
+    // memory lane), 4-channel tiles (16-byte rows, 128 KB per tile), the radix-2 stage as an extra in-place pass
+    SPX_ENTRY(16, 2, 16, 16, MODE_QUAD, 1, 512, 1, float, SPECTRE_MIX_F32),
     SPX_ENTRY(2, 16, 16, 16, MODE_QUAD, 1, 512, 1, float, SPECTRE_MIX_F32),
     SPX_ENTRY(2, 16, 16, 16, MODE_QUAD, 1, 512, 1, __nv_bfloat16, SPECTRE_MIX_BF16),
     SPX_ENTRY(2, 16, 16, 16, MODE_PAIR, 2, 512, 1, float, SPECTRE_MIX_F32),

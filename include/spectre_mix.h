@@ -203,7 +203,8 @@ int spectre_mix_set_tma(int enable);
  * exists (n_fft = 4096 fp32).  For experiments only. */
 int spectre_mix_set_tmem(int enable);
 
-/* Enable (default) / disable the two-pass path for n_fft > 4096 (falls back to the single-kernel variants). */
+/* Long transforms (n_fft > 4096): 0 = single-kernel variants only, 1 = automatic (default: the TMEM-staged single kernel where
+ * one exists -- n_fft = 8192 fp32 -- else the three-launch path around a workspace), 2 = the three-launch path wherever possible. */
 int spectre_mix_set_two_pass(int enable);
 
 /* Warp stagger before the warp-local passes: 0 = off; code > 0: hold back half of the warps by `code` nanoseconds;

@@ -801,15 +801,22 @@ def test_long_context_two_pass_and_single_kernel_agree(fb, oracle, dev):
         want = oracle.mix_flat(V, gate, n_fft, dg, mem).numpy()
         args = (V.to(dev), gate.to(dev), None if mem is None else mem.to(dev))
         try:
-            lib.spectre_mix_set_two_pass(1)
+            lib.spectre_mix_set_two_pass(2)                           # the three-launch path wherever it applies
             y2 = fb.spectral_mix(*args, n_fft=n_fft, group_width=dg)
-            lib.spectre_mix_set_two_pass(0)
+            lib.spectre_mix_set_two_pass(0)                           # single-kernel variants only
             y1 = fb.spectral_mix(*args, n_fft=n_fft, group_width=dg)
+            lib.spectre_mix_set_two_pass(1)                           # automatic (default)
+            y0 = fb.spectral_mix(*args, n_fft=n_fft, group_width=dg)
         finally:
             lib.spectre_mix_set_two_pass(1)
         _check(y2, want)
         _check(y1, want)
+        _check(y0, want)
     assert fb.plan_info(4, 16384, 16384, 768, 16)["launches"] == 3
+    # n_fft = 8192 fp32: the TMEM-staged single kernel is the default (one pass over HBM, no workspace); bf16 keeps three launches
+    info = fb.plan_info(4, 8192, 8192, 768, 16)
+    assert info["launches"] == 1 and info["workspace_bytes"] == 0 and info["radix"] == [16, 2, 16, 16] and info["tile_channels"] == 4
+    assert fb.plan_info(4, 8192, 8192, 768, 16, torch.bfloat16)["launches"] == 3
     Vb = torch.randn(1, 16384, 32, generator=torch.Generator().manual_seed(60)).to(torch.bfloat16)
     gate = torch.randn(1, 2, 8193, dtype=torch.cfloat, generator=torch.Generator().manual_seed(61))
     y = fb.spectral_mix(Vb.to(dev), gate.to(dev), n_fft=16384, group_width=16)
