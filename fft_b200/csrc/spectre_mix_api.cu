@@ -96,7 +96,7 @@ struct DeviceState {
     cudaError_t init_err = cudaSuccess;
     int sm_count = 0;
     int max_smem_optin = 0;
-    std::atomic<float2 *> twiddles[2 * (kMaxLog2N + 1)] = {};   // (log2(n_fft), radix order) -> device table (plain and SUB plans share it)
+    std::atomic<float2 *> twiddles[3 * (kMaxLog2N + 1)] = {};   // (log2(n_fft), radix order) -> device table (plain and SUB plans share it)
     std::mutex mu;                                        // table creation, occupancy cache, pool creation
     std::map<std::pair<const KernelEntry *, int>, int> occupancy;  // (entry, flags) -> CTAs/SM
     // Scratch of the two-pass long-context path when the caller passes no workspace: stream-ordered allocations
@@ -162,7 +162,10 @@ int get_device_state(DeviceState **out, int *dev_out) {
 int get_twiddles(DeviceState &st, const KernelEntry &k, const float2 **tw) {
     int lg = 0;
     while ((1 << lg) < k.n_fft) ++lg;
-    if (k.radix[0] == 16 && k.radix[1] == 2) lg += kMaxLog2N + 1;   // the radix-16-first order of n_fft = 8192 has its own table
+    // radix orders of one n_fft: (r, 16, 16 ..) | (16, 2, 16, 16) at 8192 | (16, 16, r) at 1024 / 2048: one table each
+    const int last = k.radix[3] > 1 ? k.radix[3] : (k.radix[2] > 1 ? k.radix[2] : k.radix[1]);
+    if (k.radix[0] == 16 && k.radix[1] == 2) lg += kMaxLog2N + 1;
+    else if (k.radix[0] == 16 && last != 16) lg += 2 * (kMaxLog2N + 1);
     float2 *d = st.twiddles[lg].load(std::memory_order_acquire);
     if (!d) {
         // first use of this n_fft on this device: build in double on the host, upload (synchronous -- do one warm-up call
@@ -236,8 +239,11 @@ int pick_mode(int dtype, int group_width, const void *v, long long v_sb, long lo
     return spx::MODE_REAL;
 }
 
+// B > 0: batch-aware choice between the wide-row TMEM-staged variants of n_fft = 1024 / 2048 (128 KB tiles, one CTA per SM)
+// and the narrower two-CTAs-per-SM variants: below about seven tiles per SM the launch is too short for the big tiles
+// (measured crossover: profiles/r02k_ab_wide_rows_*.txt -- 1024: batch 48, 2048: batch 16-24 at C = 768)
 int choose(const DeviceState &st, int n_fft, int dtype, int mode_max, int C, int group_width, Choice *out,
-           bool no_gate = false) {
+           bool no_gate = false, int B = 0) {
     const std::vector<KernelEntry> &reg = registry();
     const int g_tile_channels_override = ::g_tile_channels_override.load(std::memory_order_relaxed);
     // candidates in registry order (first = default) for the widest mode that has any variant
@@ -263,6 +269,9 @@ int choose(const DeviceState &st, int n_fft, int dtype, int mode_max, int C, int
             c.gate_tables = gt;
             c.tiles_per_row = (ce + k.ncol - 1) / k.ncol;
             c.smem = sm;
+            if (k.tmem_ok && n_fft < 4096 && B > 0 && !g_tile_channels_override &&
+                (long long)B * c.tiles_per_row < 7LL * st.sm_count)
+                continue;   // short launch: a narrower variant of this n_fft follows in the registry
             if (!best) { best = &k; bc = c; }
         }
         if (best) { *out = bc; return 0; }
@@ -554,7 +563,7 @@ int mix_fwd_impl(const void *v, int v_dtype, int64_t v_stride_b, int64_t v_strid
     const KernelEntry *ks = two_pass_kernel(n_fft, v_dtype, mode, group_width, mem, mem_stride);
     Choice c;
     if (!ks) {
-        if (int rc = choose(*st, n_fft, v_dtype, mode, C, group_width, &c)) return rc;
+        if (int rc = choose(*st, n_fft, v_dtype, mode, C, group_width, &c, false, B)) return rc;
     }
     // scratch of this call: [long-context intermediate][materialised gate, when this layout has no in-kernel gate generator]
     const bool fused_gate = gs && (ks ? ks->anch_ok : c.k->anch_ok);
@@ -639,12 +648,16 @@ int mix_fwd_impl(const void *v, int v_dtype, int64_t v_stride_b, int64_t v_strid
     alignas(64) CUtensorMap tmap, tmap_out;
     const int tile_ch = mode_channels(c.k->mode) * c.k->ncol;
     const bool use_tma = g_use_tma.load(std::memory_order_relaxed) != 0, use_tmem = g_use_tmem.load(std::memory_order_relaxed) != 0;
-    bool tma = use_tma && c.k->tma_ok && (int)c.k->smem_bytes(c.gate_tables, true, false) <= st->max_smem_optin &&
-               tma_layout_ok(v, v_dtype, v_stride_b, v_stride_n) && tma_layout_ok(out, out_dtype, out_stride_b, out_stride_n) &&
-               make_v_tensor_map(&tmap, v, v_dtype, v_stride_b, v_stride_n, B, n_io, C, std::min(n_fft, spx::kTmaBoxRows),
-                                 tile_ch, g_l2_promo.load(std::memory_order_relaxed)) &&
-               make_v_tensor_map(&tmap_out, out, out_dtype, out_stride_b, out_stride_n, B, n_io, C, c.k->out_box_rows, tile_ch);
-    const bool tmem = tma && use_tmem && c.k->tmem_ok && (int)c.k->smem_bytes(c.gate_tables, true, true) <= st->max_smem_optin;
+    const bool layout_ok = use_tma && c.k->tma_ok && tma_layout_ok(v, v_dtype, v_stride_b, v_stride_n) &&
+                           tma_layout_ok(out, out_dtype, out_stride_b, out_stride_n);
+    bool tmem = layout_ok && use_tmem && c.k->tmem_ok && (int)c.k->smem_bytes(c.gate_tables, true, true) <= st->max_smem_optin;
+    bool tma = layout_ok && (tmem || (int)c.k->smem_bytes(c.gate_tables, true, false) <= st->max_smem_optin) &&
+               make_v_tensor_map(&tmap, v, v_dtype, v_stride_b, v_stride_n, B, n_io, C,
+                                 tmem ? c.k->tmem_box_rows : std::min(n_fft, spx::kTmaBoxRows), tile_ch,
+                                 g_l2_promo.load(std::memory_order_relaxed)) &&
+               make_v_tensor_map(&tmap_out, out, out_dtype, out_stride_b, out_stride_n, B, n_io, C,
+                                 tmem ? c.k->tmem_box_rows : c.k->out_box_rows, tile_ch);
+    if (!tma) tmem = false;
     const int occ = std::max(1, occupancy_of(*st, c, mem != nullptr, tma, tmem));
     // paired tile order (TMEM variant): the two channel tiles of one gate group back to back, gate row staged once for both
     p.pair_tiles = (tmem && (p.sched & 16) && c.gate_tables == 1 && c.tiles_per_row % 2 == 0 && group_width % (2 * tile_ch) == 0) ? 1 : 0;
@@ -778,7 +791,7 @@ int spectre_mix_plan(int v_dtype, int out_dtype, int has_mem, int B, int N, int 
         c.k = ks;
         c.gate_tables = 2;
         c.tiles_per_row = (C / 4 + ks->ncol - 1) / ks->ncol;
-    } else if (int rc = choose(*st, n_fft, v_dtype, mode, C, group_width, &c)) return rc;
+    } else if (int rc = choose(*st, n_fft, v_dtype, mode, C, group_width, &c, false, B)) return rc;
     memset(info, 0, sizeof(*info));
     info->n_fft = n_fft;
     for (int i = 0; i < 4; ++i) info->radix[i] = c.k->radix[i];

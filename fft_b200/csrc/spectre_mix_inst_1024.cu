@@ -6,6 +6,10 @@
 namespace spx {
 namespace {
 const KernelEntry kTable[] = {
+    // wide-row TMEM-staged variant (default): 1024 = 16 x 16 x 4, 32-channel tiles = 128-byte rows, 1024 x 32 x 4 B = the same
+    // 128 KB tile, tensor-memory staging and helper warpgroup as the 4096 kernel
+    SPX_ENTRY(16, 16, 4, 1, MODE_QUAD, 8, 512, 1, float, SPECTRE_MIX_F32),
+    SPX_ENTRY(16, 16, 4, 1, MODE_QUAD, 8, 512, 1, __nv_bfloat16, SPECTRE_MIX_BF16),
     // 16-channel tiles first (default): 64-byte fp32 / 32-byte bf16 rows (measured 4160 vs 3950 GB/s fp32 at B = 256)
     SPX_ENTRY(4, 16, 16, 1, MODE_QUAD, 4, 256, 2, float, SPECTRE_MIX_F32),
     SPX_ENTRY(4, 16, 16, 1, MODE_QUAD, 4, 256, 2, __nv_bfloat16, SPECTRE_MIX_BF16),

@@ -6,6 +6,9 @@
 namespace spx {
 namespace {
 const KernelEntry kTable[] = {
+    // wide-row TMEM-staged variant (default): 2048 = 16 x 16 x 8, 16-channel tiles = 64-byte rows, 128 KB per tile
+    SPX_ENTRY(16, 16, 8, 1, MODE_QUAD, 4, 512, 1, float, SPECTRE_MIX_F32),
+    SPX_ENTRY(16, 16, 8, 1, MODE_QUAD, 4, 512, 1, __nv_bfloat16, SPECTRE_MIX_BF16),
     SPX_ENTRY(8, 16, 16, 1, MODE_QUAD, 2, 256, 2, float, SPECTRE_MIX_F32),
     SPX_ENTRY(8, 16, 16, 1, MODE_QUAD, 2, 256, 2, __nv_bfloat16, SPECTRE_MIX_BF16),
     SPX_ENTRY(8, 16, 16, 1, MODE_QUAD, 4, 512, 1, float, SPECTRE_MIX_F32),             // 16-channel tile, one CTA per SM

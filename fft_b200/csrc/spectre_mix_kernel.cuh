@@ -234,6 +234,9 @@ __host__ __device__ constexpr int cmax(int a, int b) { return a > b ? a : b; }
 #define SPX_SUB_TW_SMEM 1   // sub-transform variant: stage-0 twiddle rows in shared memory (12 KB) at the price of one ring slot
 #endif
 constexpr int kTmemSlotsMax = 7;
+constexpr int kTmaBoxRows = 256;
+// TMEM-staged variants: one ring slot = one TMA box of 512 tile elements (8 KB of fp32 rows) but at most 256 rows
+__host__ __device__ constexpr int tmem_box_rows(int ncol) { return 512 / ncol < kTmaBoxRows ? 512 / ncol : kTmaBoxRows; }
 // ring slots of a plan: the sub-transform variant holds a full-length gate table (two half-length slots) and has room for six,
 // or for five next to its stage-0 twiddle rows (measured faster: profiles/r01d_ab_sub_twiddles.txt)
 template <class PL>
@@ -427,7 +430,7 @@ struct Smem {
     // TMEM variant: ring of kTmemSlots + kTmemStoreSlots TMA boxes (256 rows each) instead of the staging buffers
     static constexpr size_t bytes(int gate_tables, bool tma = false, size_t row_bytes = 0, bool tmem = false) {
         return ((base_bytes(gate_tables) + 127) / 128) * 128 + bar_bytes +
-               (tmem ? (size_t)tmem_slots<PL>() * 256 * row_bytes : (tma ? 2 * stg_bytes(row_bytes) : 0));
+               (tmem ? (size_t)tmem_slots<PL>() * tmem_box_rows(NCOL) * row_bytes : (tma ? 2 * stg_bytes(row_bytes) : 0));
     }
 };
 
@@ -454,7 +457,8 @@ __device__ __forceinline__ void fwd_inner_pass(typename Elem<MODE>::S *buf, cons
     using V = typename E::V;
     constexpr int R = PL::R(S_), L = PL::L(S_), NBF = PL::N / R, ITEMS = NCOL * NBF;
     constexpr int CS = Smem<PL, MODE, NCOL>::CS;
-    static_assert(L % 16 == 0 || L == 1, "offset padding assumes 16 | L");
+    // pad(e0 + m L) = pad(e0) + pad(m L) needs (e0 % 16) + (m L % 16) < 16: true for 16 | L, and for L | 16 because e0 % 16 = u < L
+    static_assert(L % 16 == 0 || 16 % L == 0, "offset padding assumes 16 | L or L | 16");
     for (int w = tid; w < ITEMS; w += NT) {
         // ILV: the element columns are interleaved over adjacent lanes (both columns of a butterfly id share twiddles / gate)
         const int col = ILV ? w % NCOL : w / NBF, bf = ILV ? w / NCOL : w - col * NBF;
@@ -644,7 +648,7 @@ struct Lin {  // PAIR / REAL never use the TMA path
     static __device__ __forceinline__ T put(const Cx<float> &c) { return make_float2(c.re, c.im); }
 };
 
-constexpr int kTmaBoxRows = 256;
+
 // The TMA variant adds one producer warpgroup (one elected lane works).  A whole warpgroup, because setmaxnreg moves
 // registers between warpgroups: the producer shrinks to 24 registers and the compute warps take what it frees.
 constexpr int kProducerThreads = 128;
@@ -816,6 +820,11 @@ __global__ void __launch_bounds__(NT + ((TMA_IN && NT >= kSepProducerMinThreads)
     constexpr bool kWarpLocal = (NS >= 3) && (PL::R(NS - 1) == 16) && (PL::R(NS - 2) == 16) && (NT % 32 == 0) &&
                                 ((NCOL * (N / 16)) % NT == 0 || NT % (NCOL * (N / 16)) == 0) && ((N / 16) % 32 == 0);
 
+    // Narrow last radix (wide-row TMEM variants: 1024 = 16 x 16 x 4 with 32-channel tiles, 2048 = 16 x 16 x 8 with 16-channel
+    // tiles): stage 1 has L = RL, so the RL threads (same leading digits, u = 0 .. RL-1; adjacent lanes) of a stage-1 butterfly
+    // group produce exactly the inputs of 16 middle-pass items; giving each of them 16 / RL of those items keeps the exchange
+    // inside the warp here too (see the middle pass).
+    constexpr bool kWarpLocalN = TMEM_IO && (NS == 3) && (PL::R(1) == 16) && (RL < 16) && (16 % RL == 0) && (NCOL * (N / 16) == NT);
     // inner passes and the middle pass map (column, butterfly) -> thread with the two element columns on adjacent lanes: gate and
     // twiddle reads of a lane pair coincide (one wavefront instead of two); the exchanges stay inside a warp
     constexpr bool kIlv = (SPX_ILV != 0) && TMEM_IO && kWarpLocal && NS == 3 && NCOL == 2 && MODE == MODE_QUAD;
@@ -839,10 +848,12 @@ __global__ void __launch_bounds__(NT + ((TMA_IN && NT >= kSepProducerMinThreads)
     // TMEM_IO: the helper warpgroup parks the NEXT tile in tensor memory while this one is transformed and drains the
     // PREVIOUS tile's results from tensor memory, so loads, stores and the FFT passes of three tiles overlap although
     // shared memory holds only one.  Needs one stage-0 butterfly per thread and row blocks that are multiples of 128.
-    static_assert(!TMEM_IO || (SEP && sizeof(TIN) == sizeof(TOUT) && NT == NCOL * PL::L(0) && PL::L(0) % 128 == 0 &&
-                               MINB == 1 && (PL::N * NCOL * 4) % 128 == 0 && PL::N * NCOL * 4 / 128 * 2 <= 512),
+    static_assert(!TMEM_IO || (SEP && sizeof(TIN) == sizeof(TOUT) && NT == NCOL * PL::L(0) && (PL::L(0) * NCOL) % 128 == 0 &&
+                               128 % NCOL == 0 && MINB == 1 && (PL::N * NCOL * 4) % 128 == 0 && PL::N * NCOL * 4 / 128 * 2 <= 512),
                   "TMEM staging: unsupported shape");
-    constexpr int G128 = PL::L(0) / 128;                 // 128-row groups per stage-0 row block (column-group stride per m = G128 * NCOL)
+    // tensor-memory columns between the rows u + L(0) m and u + L(0) (m + 1) of a stage-0 butterfly: the flat element index
+    // advances by L(0) * NCOL, a multiple of 128, i.e. by L(0) * NCOL / 128 column groups of 4
+    constexpr int MSTRIDE = 4 * (PL::L(0) * NCOL / 128);
     constexpr int CPR = NCOL * 4;                        // TMEM columns per tile row (fp32 channels)
     constexpr int TCOLS = PL::N / 128 * CPR;             // TMEM columns of one parked tile (256 at 4096 x 8 ch)
     const int tid = threadIdx.x;
@@ -858,7 +869,10 @@ __global__ void __launch_bounds__(NT + ((TMA_IN && NT >= kSepProducerMinThreads)
     constexpr bool SUB = PL::kSub;
     constexpr int GKS = SUB ? N / NT : 1;           // sub-transform: full-length gate table, entries per thread
     static_assert(!SUB || (N % NT == 0 && MODE == MODE_QUAD && !RFFT_ONLY), "sub-transform variant: packed mix kernel only");
-    const bool gate_early = SUB || (p.gate_tables == 1);   // one table per tile: fetch the next tile's while this one finishes
+    // tables fetched for the NEXT tile while this one finishes (parked in registers across the inner inverse pass): one, or
+    // two on the wide tiles whose 32 channels span two 16-channel gate groups
+    constexpr int kEarlyGT = (!SUB && NCOL * CH >= 32) ? 2 : 1;
+    const bool gate_early = SUB || (p.gate_tables <= kEarlyGT);
     const TIN *vbase = reinterpret_cast<const TIN *>(p.v);
     TOUT *obase = reinterpret_cast<TOUT *>(p.out);
     const int CE = p.C / CH;  // elements per row
@@ -923,7 +937,8 @@ __global__ void __launch_bounds__(NT + ((TMA_IN && NT >= kSepProducerMinThreads)
     // stores while draining
     [[maybe_unused]] uint32_t tmem_base = 0;
     if constexpr (TMEM_IO) {
-        constexpr uint32_t SLOTB = (uint32_t)kTmaBoxRows * ROWB;           // bytes of one ring slot
+        constexpr int TBOXR = tmem_box_rows(NCOL);                         // rows per TMA box / ring slot
+        constexpr uint32_t SLOTB = (uint32_t)TBOXR * ROWB;                 // bytes of one ring slot
         const uint32_t bar_in_full = bar, bar_in_free = bar + 8, bar_out_full = bar + 16, bar_out_free = bar + 24,
                        bar_landed = bar + 32;
         uint32_t *tmem_base_s = reinterpret_cast<uint32_t *>(smem_raw + bar_off + 96);
@@ -945,8 +960,8 @@ __global__ void __launch_bounds__(NT + ((TMA_IN && NT >= kSepProducerMinThreads)
             asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kTmemHelperRegs));
             const int hl = tid - NT;                              // 0..127 = TMEM lane this helper thread serves
             const uint32_t tq = tmem_base + ((uint32_t)(hl & ~31) << 16);
-            constexpr int NBOX = N / kTmaBoxRows;                 // TMA boxes per tile
-            constexpr int GPB = kTmaBoxRows * NCOL / 128;         // 128-element groups per box
+            constexpr int NBOX = N / TBOXR;                       // TMA boxes per tile
+            constexpr int GPB = TBOXR * NCOL / 128;               // 128-element groups per box
 #ifndef SPX_TMEM_SP
 #define SPX_TMEM_SP 1
 #endif
@@ -980,7 +995,7 @@ __global__ void __launch_bounds__(NT + ((TMA_IN && NT >= kSepProducerMinThreads)
                 // (no proxy fence: the slot was last touched by shared-memory READS of the helper threads, ordered by the
                 // helper barrier, or by a TMA store whose read the store thread has waited for)
                 mbar_expect_tx(bar_landed + 8 * ld_slot, SLOTB);
-                tma_load_3d(smem_u32(stg) + ld_slot * SLOTB, (DGATE && (ld_seq & 1)) ? &tmap_out : &tmap, ld_tc, ld_k * kTmaBoxRows, ld_tb,
+                tma_load_3d(smem_u32(stg) + ld_slot * SLOTB, (DGATE && (ld_seq & 1)) ? &tmap_out : &tmap, ld_tc, ld_k * TBOXR, ld_tb,
                             bar_landed + 8 * ld_slot);
                 --ld_left;
                 ld_slot = (ld_slot + 1 == kTmemSlots) ? 0 : ld_slot + 1;
@@ -1049,7 +1064,7 @@ __global__ void __launch_bounds__(NT + ((TMA_IN && NT >= kSepProducerMinThreads)
 #if SPX_COOP_PF
                     if (pf) {
                         prefetch_l2(pf);
-                        pf += (long long)kTmaBoxRows * p.v_sn;
+                        pf += (long long)TBOXR * p.v_sn;
                     }
 #endif
 #if SPX_HELPER_TL
@@ -1083,7 +1098,7 @@ __global__ void __launch_bounds__(NT + ((TMA_IN && NT >= kSepProducerMinThreads)
                     const long long c3 = clock64();
 #endif
                     if (hl == kStoreLane && do_drain) {
-                        tma_store_3d(&tmap_out, smem_u32(slot), tc, k * kTmaBoxRows, tb);
+                        tma_store_3d(&tmap_out, smem_u32(slot), tc, k * TBOXR, tb);
                         tma_commit();
                         tma_wait_read<SP>();                       // the store of step - SP has left its slot
                     }
@@ -1227,7 +1242,7 @@ __global__ void __launch_bounds__(NT + ((TMA_IN && NT >= kSepProducerMinThreads)
             Cx<V> x0[ITERS0][R0];
             if constexpr (TMEM_IO) {
                 // the helper warpgroup parked this tile in TMEM-IN: row u + L0 m sits in lane u % 128, column group
-                // (u / 128 + G128 m); this warp's 32 lanes are exactly its 32 values of u
+                // ((u NCOL + col) / 128 + MSTRIDE / 4 * m); this warp's 32 lanes are exactly its 32 (column, u) pairs
                 if (!(p.sched & 8)) mbar_wait(bar, tile_it & 1);
                 tc_fence_after();
                 SPX_MARK(1)
@@ -1236,7 +1251,7 @@ __global__ void __launch_bounds__(NT + ((TMA_IN && NT >= kSepProducerMinThreads)
                 const uint32_t ta = tmem_base + ((uint32_t)(32 * ((tid >> 5) & 3)) << 16) + (uint32_t)(4 * ((u * NCOL + col) >> 7));
 #pragma unroll
                 for (int m = 0; m < R0; ++m)
-                    tmem_ld4(ta + (uint32_t)(m * G128 * CPR), x0[0][m].re.x, x0[0][m].re.y, x0[0][m].im.x, x0[0][m].im.y);
+                    tmem_ld4(ta + (uint32_t)(m * MSTRIDE), x0[0][m].re.x, x0[0][m].re.y, x0[0][m].im.x, x0[0][m].im.y);
                 tmem_wait_ld();
                 tc_fence_before();
                 __syncwarp();
@@ -1248,7 +1263,7 @@ __global__ void __launch_bounds__(NT + ((TMA_IN && NT >= kSepProducerMinThreads)
                     const uint32_t tb_ = ta + (uint32_t)TCOLS;
 #pragma unroll
                     for (int m = 0; m < R0; ++m)
-                        tmem_st4(tb_ + (uint32_t)(m * G128 * CPR), x0[0][m].re.x, x0[0][m].re.y, x0[0][m].im.x, x0[0][m].im.y);
+                        tmem_st4(tb_ + (uint32_t)(m * MSTRIDE), x0[0][m].re.x, x0[0][m].re.y, x0[0][m].im.x, x0[0][m].im.y);
                     tmem_wait_st();
                     tc_fence_before();
                     __syncwarp();
@@ -1335,15 +1350,27 @@ __global__ void __launch_bounds__(NT + ((TMA_IN && NT >= kSepProducerMinThreads)
         // The exchange between stage NS-2 and the middle pass is a 16x16 transpose among the 16 threads that share
         // (column, leading digits): with consecutive butterflies on consecutive lanes those threads are one half-warp,
         // in this pass and in the middle pass alike, so __syncwarp() orders it and warps run on unsynchronised.
-        if constexpr (NS > 2) { fwd_inner_pass<PL, MODE, NCOL, NT, 1, kIlv>(buf, tw, p.tw, tid); if constexpr (NS == 3 && kWarpLocal) __syncwarp(); else cta_sync<NT, SEP>(); }
+        if constexpr (NS > 2) { fwd_inner_pass<PL, MODE, NCOL, NT, 1, kIlv>(buf, tw, p.tw, tid); if constexpr (NS == 3 && (kWarpLocal || kWarpLocalN)) __syncwarp(); else cta_sync<NT, SEP>(); }
         if constexpr (NS > 3) { fwd_inner_pass<PL, MODE, NCOL, NT, 2, kIlv>(buf, tw, p.tw, tid); if constexpr (kWarpLocal) __syncwarp(); else cta_sync<NT, SEP>(); }
 
         SPX_MARK(3)
         // ---- middle pass: last forward butterfly -> gate (+memory) -> first inverse butterfly
         {
             constexpr int NBF = N / RL, ITEMS = NCOL * NBF;
-            for (int w = tid; w < ITEMS; w += NT) {
-                const int col = kIlv ? w % NCOL : w / NBF, Q = kIlv ? w / NCOL : w - col * NBF;
+            constexpr int IPT = kWarpLocalN ? 16 / RL : 1;      // narrow-radix mapping: middle-pass items per thread
+            for (int w = tid, jj = 0; kWarpLocalN ? (jj < IPT) : (w < ITEMS); w += NT, ++jj) {
+                int col, Q;
+                if constexpr (kWarpLocalN) {
+                    // this thread's stage-1 butterfly is (col, Qf, u); the group's 16 items are 16 Qf + q, thread u takes
+                    // q = IPT u + jj: consecutive lanes 16 elements apart (conflict-free with the 16-byte pad per 16 elements)
+                    constexpr int NB1 = N / 16;
+                    col = tid / NB1;
+                    const int bf1 = tid - col * NB1, Qf = bf1 / RL, u1 = bf1 - Qf * RL;
+                    Q = 16 * Qf + IPT * u1 + jj;
+                } else {
+                    col = kIlv ? w % NCOL : w / NBF;
+                    Q = kIlv ? w / NCOL : w - col * NBF;
+                }
                 if ((ce0 + col) >= CE) continue;   // column past the last channel: nothing to transform
                 const int e0 = Q * RL;
                 S *cb = buf + col * CS + e0 + (e0 >> 4);
@@ -1471,13 +1498,14 @@ __global__ void __launch_bounds__(NT + ((TMA_IN && NT >= kSepProducerMinThreads)
             ++tile_it;
             continue;
         }
-        if constexpr (kWarpLocal && !RFFT_ONLY) __syncwarp(); else cta_sync<NT, SEP>();
+        if constexpr ((kWarpLocal || kWarpLocalN) && !RFFT_ONLY) __syncwarp(); else cta_sync<NT, SEP>();
         SPX_MARK(4)
         if constexpr (RFFT_ONLY) continue;
 
         // the gate table is free again: start fetching the next tile's gate row, park it in registers
         // across the inner inverse passes, and publish it before the last pass
         float2 gnext[SUB ? GKS : (SPX_GATE_ASYNC ? 1 : GK)];
+        [[maybe_unused]] float2 gnext2[kEarlyGT == 2 ? GK : 1];   // second table of a wide tile
         const bool fetch_next = gate_early && tile_next_ < p.num_tiles && !partner_next;   // the partner tile reuses the table
         int nq = 0;
         if (fetch_next) {
@@ -1489,6 +1517,9 @@ __global__ void __launch_bounds__(NT + ((TMA_IN && NT >= kSepProducerMinThreads)
             } else {
 #if !SPX_GATE_ASYNC
                 gate_fetch<N, NT, GK>(gnext, gate_row<ANCH>(p, nrow, ng, N / 2 + 1), tid);
+                if constexpr (kEarlyGT == 2) {
+                    if (p.gate_tables == 2 && ng + 1 < p.NG) gate_fetch<N, NT, GK>(gnext2, gate_row<ANCH>(p, nrow, ng + 1, N / 2 + 1), tid);
+                }
 #endif
             }
         }
@@ -1507,6 +1538,9 @@ __global__ void __launch_bounds__(NT + ((TMA_IN && NT >= kSepProducerMinThreads)
                 gate_copy_async<N, NT, GK>(gate_s, p.gate + ((long long)nrow * p.NG + ng) * (N / 2 + 1), tid);
 #else
                 gate_put<N, NT, GK>(gate_s, gnext, tid, p.inv_n);
+                if constexpr (kEarlyGT == 2) {
+                    if (p.gate_tables == 2 && gdiv(ncol_ * NCOL * CH) + 1 < p.NG) gate_put<N, NT, GK>(gate_s + GS, gnext2, tid, p.inv_n);
+                }
 #endif
             }
         }
@@ -1574,7 +1608,7 @@ __global__ void __launch_bounds__(NT + ((TMA_IN && NT >= kSepProducerMinThreads)
 #pragma unroll
                 for (int m = 0; m < R0; ++m) {
                     const Cx<V> y = cswap(x0[0][m]);
-                    tmem_st4(ta + (uint32_t)(m * G128 * CPR), y.re.x, y.re.y, y.im.x, y.im.y);
+                    tmem_st4(ta + (uint32_t)(m * MSTRIDE), y.re.x, y.re.y, y.im.x, y.im.y);
                 }
                 tmem_wait_st();
                 tc_fence_before();

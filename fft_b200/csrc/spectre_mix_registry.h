@@ -19,6 +19,7 @@ struct KernelEntry {
     int twn;       // twiddle table entries
     size_t (*smem_bytes)(int gate_tables, bool tma, bool tmem);
     int out_box_rows;   // rows per TMA store box (TMA variant)
+    int tmem_box_rows;  // rows per TMA box, loads and stores, of the TMEM-staged variant
     // tmap != nullptr selects the TMA-fed variant (only when tma_ok)
     // p.gate == nullptr selects the in-kernel gate generator (p.gsrc = anchors; only when anch_ok)
     cudaError_t (*launch)(const MixParams &p, int grid, bool has_mem, const CUtensorMap *tmap_in, const CUtensorMap *tmap_out,
@@ -44,7 +45,7 @@ struct Launcher {
     static constexpr bool kTma = (MODE == MODE_QUAD) && ((sizeof(TIO) * 4 * NCOL) % 16 == 0);
     // TMEM staging: packed tiles (fp32 or bf16 in HBM, fp32 in tensor memory), one stage-0 butterfly per thread, 1 CTA per SM, two tiles fit the 512 columns
     static constexpr bool kTmem = kTma && NT >= kSepProducerMinThreads && NT == NCOL * PL::L(0) &&
-                                  PL::L(0) % 128 == 0 && MINB == 1 && (PL::N * NCOL * 4 / 128 * 2 <= 512);
+                                  (PL::L(0) * NCOL) % 128 == 0 && 128 % NCOL == 0 && MINB == 1 && (PL::N * NCOL * 4 / 128 * 2 <= 512);
     // in-kernel gate generation (spectre_mix_fwd_anchors): built for the packed mode, the layout of every Spectre model with
     // 4 | group_width; other layouts take the materialised-gate kernels behind spectre_gate_expand
     static constexpr bool kAnch = (MODE == MODE_QUAD);
@@ -90,7 +91,7 @@ struct Launcher {
         return cudaLaunchKernel(f, dim3(grid), dim3(NT), args, sm, st);
     }
     static cudaError_t launch_dgate(const MixParams &p, int grid, const CUtensorMap *tmap_v, const CUtensorMap *tmap_dy, cudaStream_t st) {
-        if constexpr (kTmem && PL::NS == 3 && !PL::kSub) {
+        if constexpr (kTmem && PL::NS == 3 && !PL::kSub && PL::R(2) == 16) {
             const size_t sm = smem_bytes(1, true, true);
             const void *f = reinterpret_cast<const void *>(
                 &spectre_mix_kernel<PL, MODE, NCOL, NT, MINB, TIO, TIO, false, false, true, true, false, true>);
@@ -104,7 +105,7 @@ struct Launcher {
             return cudaErrorNotSupported;
         }
     }
-    static constexpr bool kDgate = kTmem && PL::NS == 3 && !PL::kSub;
+    static constexpr bool kDgate = kTmem && PL::NS == 3 && !PL::kSub && PL::R(2) == 16;
     static int occupancy(int gate_tables, bool has_mem, bool tma, bool tmem) {
         const size_t sm = smem_bytes(gate_tables, tma, tmem);
         const void *f = pick(has_mem, tma, tmem);
@@ -137,7 +138,7 @@ struct RfftPtr<PL, MODE_REAL, NCOL, NT, MINB, TIO> {
         (R0) * (R1) * (R2) * (R3), {R0, R1, R2, R3}, MODE, IOCODE, NCOL, NT, MINB,                            \
             ::spx::Plan<R0, R1, R2, R3>::TWN,                                                                 \
             &::spx::Launcher<::spx::Plan<R0, R1, R2, R3>, MODE, NCOL, NT, MINB, TIO>::smem_bytes,             \
-            ::spx::Smem<::spx::Plan<R0, R1, R2, R3>, MODE, NCOL>::OUT_BOX_ROWS,                               \
+            ::spx::Smem<::spx::Plan<R0, R1, R2, R3>, MODE, NCOL>::OUT_BOX_ROWS, ::spx::tmem_box_rows(NCOL),   \
             &::spx::Launcher<::spx::Plan<R0, R1, R2, R3>, MODE, NCOL, NT, MINB, TIO>::launch,                 \
             &::spx::Launcher<::spx::Plan<R0, R1, R2, R3>, MODE, NCOL, NT, MINB, TIO>::occupancy,              \
             ::spx::Launcher<::spx::Plan<R0, R1, R2, R3>, MODE, NCOL, NT, MINB, TIO>::kTma ? 1 : 0,            \
@@ -153,7 +154,7 @@ struct RfftPtr<PL, MODE_REAL, NCOL, NT, MINB, TIO> {
         (R0) * (R1) * (R2) * (R3), {R0, R1, R2, R3}, MODE, IOCODE, NCOL, NT, MINB,                            \
             ::spx::Plan<R0, R1, R2, R3, true>::TWN,                                                           \
             &::spx::Launcher<::spx::Plan<R0, R1, R2, R3, true>, MODE, NCOL, NT, MINB, TIO>::smem_bytes,       \
-            ::spx::Smem<::spx::Plan<R0, R1, R2, R3, true>, MODE, NCOL>::OUT_BOX_ROWS,                         \
+            ::spx::Smem<::spx::Plan<R0, R1, R2, R3, true>, MODE, NCOL>::OUT_BOX_ROWS, ::spx::tmem_box_rows(NCOL), \
             &::spx::Launcher<::spx::Plan<R0, R1, R2, R3, true>, MODE, NCOL, NT, MINB, TIO>::launch,           \
             &::spx::Launcher<::spx::Plan<R0, R1, R2, R3, true>, MODE, NCOL, NT, MINB, TIO>::occupancy,        \
             ::spx::Launcher<::spx::Plan<R0, R1, R2, R3, true>, MODE, NCOL, NT, MINB, TIO>::kTma ? 1 : 0,      \
