@@ -34,12 +34,13 @@ template <class TIO>
 __device__ __forceinline__ void store_quad(TIO *p, const Cx<float2> &c) { GIO<MODE_QUAD, TIO>::store(p, c); }
 
 // PRE: user V -> scratch;  POST: scratch -> user out.  sub = 4096 rows per sub-transform.
+// twid: W_N^{u q} for q = 1 .. R-1, u < sub, built on the host in double ([q-1][u]; 64 KB / 96 KB for R = 2 / 4, L2-resident:
+// every thread of a row reads the same R-1 entries)
 template <int R, class TIO, bool PRE>
 __global__ void __launch_bounds__(256) long_pass_kernel(const void *src_, void *dst_, long long u_sb, long long u_sn, int B, int rows,
-                                                        int C, int sub) {
+                                                        int C, int sub, const float2 *__restrict__ twid) {
     const int CQ = C / 4;
     const long long items = (long long)B * sub * CQ;
-    const float inv_n = 1.0f / (float)(R * sub);
     for (long long it = (long long)blockIdx.x * blockDim.x + threadIdx.x; it < items; it += (long long)gridDim.x * blockDim.x) {
         const int cq = (int)(it % CQ);
         const long long r = it / CQ;
@@ -60,13 +61,12 @@ __global__ void __launch_bounds__(256) long_pass_kernel(const void *src_, void *
 #pragma unroll
             for (int q = 0; q < R; ++q) x[q] = cswap(load_quad<float>(src + (long long)q * sub * C));
         }
-        // twiddles W_N^{u q}: the angle -2 pi u q / N is exact in float32 (u q < 2^24, N a power of two); the inverse
-        // side works on (im, re)-swapped data, where multiplying by W is multiplying the true value by conj(W)
+        // twiddles W_N^{u q} from the table; the inverse side works on (im, re)-swapped data, where multiplying by W is
+        // multiplying the true value by conj(W)
 #pragma unroll
         for (int q = 1; q < R; ++q) {
-            float s, c;
-            sincospif(-2.0f * (float)(u * q) * inv_n, &s, &c);
-            x[q] = cmul(x[q], c, s);
+            const float2 w = __ldg(twid + (size_t)(q - 1) * sub + u);
+            x[q] = cmul(x[q], w.x, w.y);
         }
         if (PRE) {
             float *dst = reinterpret_cast<float *>(dst_) + ((long long)b * R * sub + u) * C + cq * 4;
@@ -86,20 +86,20 @@ __global__ void __launch_bounds__(256) long_pass_kernel(const void *src_, void *
 
 template <int R, class TIO, bool PRE>
 cudaError_t launch_one(const void *src, void *dst, long long u_sb, long long u_sn, int B, int rows, int C, int sub, int sms,
-                       cudaStream_t st) {
+                       const float2 *twid, cudaStream_t st) {
     const long long items = (long long)B * sub * (C / 4);
     long long blocks = (items + 255) / 256;
     const long long cap = (long long)sms * 16;
     if (blocks > cap) blocks = cap;
-    long_pass_kernel<R, TIO, PRE><<<(int)blocks, 256, 0, st>>>(src, dst, u_sb, u_sn, B, rows, C, sub);
+    long_pass_kernel<R, TIO, PRE><<<(int)blocks, 256, 0, st>>>(src, dst, u_sb, u_sn, B, rows, C, sub, twid);
     return cudaGetLastError();
 }
 
 }  // namespace
 
 cudaError_t long_pass(bool pre, int R, int dtype_bf16, const void *src, void *dst, long long u_sb, long long u_sn, int B, int rows,
-                      int C, int sub, int sms, cudaStream_t st) {
-#define SPX_LP(RR, T, P) return launch_one<RR, T, P>(src, dst, u_sb, u_sn, B, rows, C, sub, sms, st)
+                      int C, int sub, int sms, const float2 *twid, cudaStream_t st) {
+#define SPX_LP(RR, T, P) return launch_one<RR, T, P>(src, dst, u_sb, u_sn, B, rows, C, sub, sms, twid, st)
     if (R == 2) {
         if (dtype_bf16) { if (pre) SPX_LP(2, __nv_bfloat16, true); else SPX_LP(2, __nv_bfloat16, false); }
         else { if (pre) SPX_LP(2, float, true); else SPX_LP(2, float, false); }

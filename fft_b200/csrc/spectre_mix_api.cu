@@ -97,6 +97,7 @@ struct DeviceState {
     int sm_count = 0;
     int max_smem_optin = 0;
     std::atomic<float2 *> twiddles[3 * (kMaxLog2N + 1)] = {};   // (log2(n_fft), radix order) -> device table (plain and SUB plans share it)
+    std::atomic<float2 *> long_tw[5] = {};                // R (2, 4) -> twiddles of the long-context streaming passes
     std::mutex mu;                                        // table creation, occupancy cache, pool creation
     std::map<std::pair<const KernelEntry *, int>, int> occupancy;  // (entry, flags) -> CTAs/SM
     // Scratch of the two-pass long-context path when the caller passes no workspace: stream-ordered allocations
@@ -180,6 +181,32 @@ int get_twiddles(DeviceState &st, const KernelEntry &k, const float2 **tw) {
             e = cudaMemcpy(d, h.data(), h.size() * sizeof(float2), cudaMemcpyHostToDevice);
             if (e != cudaSuccess) { cudaFree(d); return cuda_fail(e, "cudaMemcpy(twiddles)"); }
             st.twiddles[lg].store(d, std::memory_order_release);
+        }
+    }
+    *tw = d;
+    return 0;
+}
+
+// W_{R 4096}^{u q}, q = 1 .. R-1, u < 4096, for the pre / post passes of the three-launch long-context path
+int get_long_twiddles(DeviceState &st, int R, const float2 **tw) {
+    float2 *d = st.long_tw[R].load(std::memory_order_acquire);
+    if (!d) {
+        std::lock_guard<std::mutex> lock(st.mu);
+        d = st.long_tw[R].load(std::memory_order_acquire);
+        if (!d) {
+            const int sub = 4096;
+            const long long N = (long long)R * sub;
+            std::vector<float2> h((size_t)(R - 1) * sub);
+            for (int q = 1; q < R; ++q)
+                for (int u = 0; u < sub; ++u) {
+                    const double ang = -2.0 * M_PI * (double)(((long long)u * q) % N) / (double)N;
+                    h[(size_t)(q - 1) * sub + u] = make_float2((float)cos(ang), (float)sin(ang));
+                }
+            cudaError_t e = cudaMalloc(&d, h.size() * sizeof(float2));
+            if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(long-context twiddles)");
+            e = cudaMemcpy(d, h.data(), h.size() * sizeof(float2), cudaMemcpyHostToDevice);
+            if (e != cudaSuccess) { cudaFree(d); return cuda_fail(e, "cudaMemcpy(long-context twiddles)"); }
+            st.long_tw[R].store(d, std::memory_order_release);
         }
     }
     *tw = d;
@@ -364,7 +391,9 @@ int mix_two_pass_rows(DeviceState &st, const KernelEntry &k, const void *v, int 
                       const spx::GateSrc *gs, const void *mem, long long mem_stride, void *out, long long o_sb, long long o_sn, int B,
                       int n_io, int n_fft, int C, int group_width, float *scr, cudaStream_t stream) {
     const int sub = 4096, R = n_fft / sub;
-    cudaError_t e = spx::long_pass(true, R, dtype == SPECTRE_MIX_BF16, v, scr, v_sb, v_sn, B, n_io, C, sub, st.sm_count, stream);
+    const float2 *ltw = nullptr;
+    if (int rc = get_long_twiddles(st, R, &ltw)) return rc;
+    cudaError_t e = spx::long_pass(true, R, dtype == SPECTRE_MIX_BF16, v, scr, v_sb, v_sn, B, n_io, C, sub, st.sm_count, ltw, stream);
     if (e != cudaSuccess) return cuda_fail(e, "long-context pre pass");
 
     const float2 *tw = nullptr;
@@ -415,7 +444,7 @@ int mix_two_pass_rows(DeviceState &st, const KernelEntry &k, const void *v, int 
     e = k.launch(p, grid, mem != nullptr, tma ? &tmap : nullptr, tma ? &tmap_out : nullptr, tmem, stream);
     if (e != cudaSuccess) return cuda_fail(e, "long-context sub-transform kernel");
 
-    e = spx::long_pass(false, R, dtype == SPECTRE_MIX_BF16, scr, out, o_sb, o_sn, B, n_io, C, sub, st.sm_count, stream);
+    e = spx::long_pass(false, R, dtype == SPECTRE_MIX_BF16, scr, out, o_sb, o_sn, B, n_io, C, sub, st.sm_count, ltw, stream);
     if (e != cudaSuccess) return cuda_fail(e, "long-context post pass");
     return 0;
 }

@@ -403,6 +403,32 @@ def test_plan_info(fb):
     assert info["launches"] == 1 and info["grid"] >= 1
 
 
+def test_plan_is_batch_aware_for_wide_row_variants(fb):
+    """seq 1024 / 2048: the wide-row TMEM-staged variants (32- / 16-channel tiles, one CTA per SM) from about seven tiles per SM
+    on, the narrower two-CTAs-per-SM variants for shorter launches."""
+    assert fb.plan_info(256, 1024, 1024, 768, 16)["tile_channels"] == 32 and fb.plan_info(256, 1024, 1024, 768, 16)["radix"] == [16, 16, 4]
+    assert fb.plan_info(32, 1024, 1024, 768, 16)["tile_channels"] == 16 and fb.plan_info(32, 1024, 1024, 768, 16)["radix"] == [4, 16, 16]
+    assert fb.plan_info(128, 2048, 2048, 768, 16)["tile_channels"] == 16 and fb.plan_info(128, 2048, 2048, 768, 16)["radix"] == [16, 16, 8]
+    assert fb.plan_info(8, 2048, 2048, 768, 16)["tile_channels"] == 8
+
+
+def test_wide_row_variants_against_oracle(fb, oracle, dev):
+    """The wide-row variants at batch sizes that select them, with memory, ragged N, ragged channel tiles (C not a multiple of the
+    tile width), group widths 8 / 16 / 32 (4, 2 and 1 gate tables per 32-channel tile) and bf16."""
+    for (B, N, n_fft, C, dg, with_mem) in [(44, 1024, 1024, 768, 16, False), (12, 1000, 1024, 3112, 8, True),
+                                           (32, 1024, 1024, 1056, 32, False), (22, 2048, 2048, 784, 16, True),
+                                           (11, 2000, 2048, 1608, 8, False)]:
+        V, gate, mem = _rand_case(B, N, n_fft, C, dg, with_mem, seed=400 + C)
+        info = fb.plan_info(B, N, n_fft, C, dg)
+        assert info["radix"][0] == 16 and info["radix"][-1] in (4, 8), info          # the wide-row plan was chosen
+        got = fb.spectral_mix(V.to(dev), gate.to(dev), None if mem is None else mem.to(dev), n_fft=n_fft, group_width=dg)
+        _check(got[:3], oracle.mix_flat(V[:3], gate[:3], n_fft, dg, mem).numpy())
+        _check(got[-2:], oracle.mix_flat(V[-2:], gate[-2:], n_fft, dg, mem).numpy())
+    V, gate, _ = _rand_case(50, 1024, 1024, 768, 16, False, seed=410)
+    got = fb.spectral_mix(V.to(dev).to(torch.bfloat16), gate.to(dev), n_fft=1024, group_width=16)
+    _check(got[:2], oracle.mix_flat(V[:2].to(torch.bfloat16).float(), gate[:2], 1024, 16).numpy(), rl2=REL_L2_BF16, mabs=2e-2)
+
+
 def test_autograd_matches_oracle(fb, oracle, dev):
     """Backward of the op against autograd through the oracle's torch.fft path."""
     for (B, N, n_fft, C, dg) in [(2, 128, 128, 16, 4), (2, 100, 128, 16, 8), (1, 1024, 1024, 16, 16)]:
