@@ -58,6 +58,7 @@ class PlanInfo(ctypes.Structure):
         ("launches", ctypes.c_int),
         ("algorithmic_bytes", ctypes.c_int64),
         ("workspace_bytes", ctypes.c_int64),
+        ("dit", ctypes.c_int),
     ]
 
 

@@ -278,7 +278,7 @@ int choose(const DeviceState &st, int n_fft, int dtype, int mode_max, int C, int
         const KernelEntry *best = nullptr;
         Choice bc;
         for (const KernelEntry &k : reg) {
-            if (k.n_fft != n_fft || k.io != dtype || k.mode != mode || k.sub) continue;
+            if (k.n_fft != n_fft || k.io != dtype || k.mode != mode || k.sub || k.dit) continue;
             const int ch = mode_channels(mode);
             const int tw = ch * k.ncol;  // channels per tile
             if (g_tile_channels_override && tw != g_tile_channels_override) continue;
@@ -378,6 +378,78 @@ bool make_v_tensor_map(CUtensorMap *tm, const void *v, int dtype, long long v_sb
 }
 
 
+// DIT2 variant: V / out seen as [B][n][parity][C] (row = 2 n + parity), box {tile channels, 2, box_rows, 1}
+bool make_dit_tensor_map(CUtensorMap *tm, const void *v, int dtype, long long v_sb, long long v_sn, int B, int rows, int C,
+                         int box_rows, int tile_channels, int l2_promo = 0) {
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc || (rows & 1)) return false;
+    const cuuint64_t es = dtype == SPECTRE_MIX_F32 ? 4 : 2;
+    cuuint64_t dims[4] = {(cuuint64_t)C, 2, (cuuint64_t)(rows / 2), (cuuint64_t)B};
+    cuuint64_t strides[3] = {(cuuint64_t)v_sn * es, (cuuint64_t)v_sn * es * 2, (cuuint64_t)v_sb * es};
+    cuuint32_t box[4] = {(cuuint32_t)tile_channels, 2, (cuuint32_t)box_rows, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(tm, dtype == SPECTRE_MIX_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4,
+                     const_cast<void *>(v), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                     l2_promo == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
+                                   : (l2_promo == 2 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B
+                                                    : (l2_promo == 3 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_NONE)),
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
+// the DIT2 kernel of a transform length (n_fft = 2 * its sub-transform), if this call can take it: packed layout, even row
+// count (rows pair up as (2 n, 2 n + 1)), TMA + TMEM staging on, not switched off (sched bit 5 = experiments)
+const KernelEntry *dit_kernel(const DeviceState &st, int n_fft, int dtype, int mode, int n_io, const void *mem, long long mem_stride) {
+    if (mode != spx::MODE_QUAD || (n_io & 1) || g_use_two_pass.load(std::memory_order_relaxed) == 2) return nullptr;
+    if (!g_use_tma.load(std::memory_order_relaxed) || !g_use_tmem.load(std::memory_order_relaxed)) return nullptr;
+    if (g_tile_channels_override.load(std::memory_order_relaxed) || (g_sched.load(std::memory_order_relaxed) & 32)) return nullptr;
+    if (mem && (mem_stride % 2 != 0)) return nullptr;
+    for (const KernelEntry &k : registry())
+        if (k.dit == 2 && 2 * k.n_fft == n_fft && k.io == dtype && k.mode == spx::MODE_QUAD && k.tmem_ok &&
+            (int)k.smem_bytes(2, true, true) <= st.max_smem_optin)
+            return &k;
+    return nullptr;
+}
+
+int mix_dit(DeviceState &st, const KernelEntry &k, const void *v, int dtype, long long v_sb, long long v_sn, const void *gate,
+            const spx::GateSrc *gs, const void *mem, long long mem_stride, void *out, long long o_sb, long long o_sn, int B, int n_io,
+            int n_fft, int C, int group_width, cudaStream_t stream) {
+    const float2 *tw = nullptr;
+    if (int rc = get_twiddles(st, k, &tw)) return rc;
+    MixParams p;
+    memset(&p, 0, sizeof(p));
+    p.v = v;
+    p.out = out;
+    p.gate = reinterpret_cast<const float2 *>(gate);
+    if (gs) p.gsrc = *gs;
+    p.mem = reinterpret_cast<const float2 *>(mem);
+    p.tw = tw;
+    p.v_sb = v_sb; p.v_sn = v_sn; p.o_sb = o_sb; p.o_sn = o_sn;
+    p.mem_stride = mem_stride;
+    p.B = B;
+    p.n_in = p.n_out = n_io / 2;               // rows of each of the two interleaved sub-sequences
+    p.C = C;
+    p.group_width = group_width;
+    p.NG = C / group_width;
+    p.tiles_per_row = C / 4;                   // one 4-channel group per tile, its even and odd rows are the two tile columns
+    p.num_tiles = B * p.tiles_per_row;
+    p.gate_tables = 2;                         // half spectrum of the 2 N-point transform = two table slots
+    p.inv_n = 1.0f / (float)n_fft;
+    p.prefetch = 0;
+    p.skew_ns = g_skew_ns.load(std::memory_order_relaxed);
+    p.sched = g_sched.load(std::memory_order_relaxed) & ~(16 | 8 | 4);
+    p.sub_R = 1;
+    p.gw_shift = ilog2_exact(group_width);
+    alignas(64) CUtensorMap tmap, tmap_out;
+    if (!make_dit_tensor_map(&tmap, v, dtype, v_sb, v_sn, B, n_io, C, k.tmem_box_rows, 4, g_l2_promo.load(std::memory_order_relaxed)) ||
+        !make_dit_tensor_map(&tmap_out, out, dtype, o_sb, o_sn, B, n_io, C, k.tmem_box_rows, 4))
+        return fail(SPECTRE_MIX_ERR_UNSUPPORTED, "cuTensorMapEncodeTiled (rank 4) failed");
+    const int grid = std::min(p.num_tiles, st.sm_count);
+    cudaError_t e = k.launch(p, grid, mem != nullptr, &tmap, &tmap_out, true, stream);
+    if (e != cudaSuccess) return cuda_fail(e, "DIT2 kernel launch");
+    return 0;
+}
+
 // ---------------------------------------------------------------- long-context two-pass path (n_fft = 8192, 16384)
 const KernelEntry *find_sub_kernel() {
     for (const KernelEntry &k : registry())
@@ -468,7 +540,7 @@ const KernelEntry *two_pass_kernel(int n_fft, int dtype, int mode, int group_wid
         !g_tile_channels_override.load(std::memory_order_relaxed)) {
         // the packed layout is 16-byte aligned by construction, so a TMEM-staged variant can always take it
         for (const KernelEntry &k : registry())
-            if (k.n_fft == n_fft && k.io == dtype && k.mode == spx::MODE_QUAD && !k.sub) {
+            if (k.n_fft == n_fft && k.io == dtype && k.mode == spx::MODE_QUAD && !k.sub && !k.dit) {
                 if (k.tmem_ok && group_width % (4 * k.ncol) == 0) return nullptr;   // the default (first) packed variant is TMEM-staged
                 break;
             }
@@ -589,9 +661,13 @@ int mix_fwd_impl(const void *v, int v_dtype, int64_t v_stride_b, int64_t v_strid
 
     const int mode = pick_mode(v_dtype, group_width, v, v_stride_b, v_stride_n, out, out_stride_b, out_stride_n, mem,
                                mem_stride);
-    const KernelEntry *ks = two_pass_kernel(n_fft, v_dtype, mode, group_width, mem, mem_stride);
+    const bool layout_tma = tma_layout_ok(v, v_dtype, v_stride_b, v_stride_n) && tma_layout_ok(out, out_dtype, out_stride_b, out_stride_n);
+    const KernelEntry *kd = (n_fft > 4096 && layout_tma) ? dit_kernel(*st, n_fft, v_dtype, mode, n_io, mem, mem_stride) : nullptr;
+    const KernelEntry *ks = kd ? nullptr : two_pass_kernel(n_fft, v_dtype, mode, group_width, mem, mem_stride);
     Choice c;
-    if (!ks) {
+    if (kd) {
+        c.k = kd;
+    } else if (!ks) {
         if (int rc = choose(*st, n_fft, v_dtype, mode, C, group_width, &c, false, B)) return rc;
     }
     // scratch of this call: [long-context intermediate][materialised gate, when this layout has no in-kernel gate generator]
@@ -635,6 +711,10 @@ int mix_fwd_impl(const void *v, int v_dtype, int64_t v_stride_b, int64_t v_strid
         gate = gbuf;
         gs = nullptr;
     }
+    // n_fft = 8192: the 4096-point kernel on (even rows, odd rows) tiles with the radix-2 combine in its middle pass
+    if (kd)
+        return finish(mix_dit(*st, *kd, v, v_dtype, v_stride_b, v_stride_n, gate, gs, mem, mem_stride, out, out_stride_b,
+                              out_stride_n, B, n_io, n_fft, C, group_width, stream));
     // long transforms: one streaming radix-R pass, R interleaved 4096-point transforms in shared memory, one streaming pass
     if (ks)
         return finish(mix_two_pass(*st, *ks, v, v_dtype, v_stride_b, v_stride_n, gate, gs, mem, mem_stride, out, out_stride_b,
@@ -813,10 +893,15 @@ int spectre_mix_plan(int v_dtype, int out_dtype, int has_mem, int B, int N, int 
     DeviceState *st = nullptr;
     if (int rc = get_device_state(&st, nullptr)) return rc;
     const int mode = (group_width % 4 == 0) ? spx::MODE_QUAD : ((group_width % 2 == 0) ? spx::MODE_PAIR : spx::MODE_REAL);
-    const KernelEntry *ks = two_pass_kernel(n_fft, v_dtype, mode, group_width, nullptr, 0);
+    const KernelEntry *kd = (n_fft > 4096) ? dit_kernel(*st, n_fft, v_dtype, mode, std::min(N, n_fft), nullptr, 0) : nullptr;
+    const KernelEntry *ks = kd ? nullptr : two_pass_kernel(n_fft, v_dtype, mode, group_width, nullptr, 0);
     const bool g_use_tma = ::g_use_tma.load(std::memory_order_relaxed) != 0, g_use_tmem = ::g_use_tmem.load(std::memory_order_relaxed) != 0;
     Choice c;
-    if (ks) {
+    if (kd) {
+        c.k = kd;
+        c.gate_tables = 2;
+        c.tiles_per_row = C / 4;
+    } else if (ks) {
         c.k = ks;
         c.gate_tables = 2;
         c.tiles_per_row = (C / 4 + ks->ncol - 1) / ks->ncol;
@@ -824,7 +909,8 @@ int spectre_mix_plan(int v_dtype, int out_dtype, int has_mem, int B, int N, int 
     memset(info, 0, sizeof(*info));
     info->n_fft = n_fft;
     for (int i = 0; i < 4; ++i) info->radix[i] = c.k->radix[i];
-    info->tile_channels = mode_channels(c.k->mode) * c.k->ncol;
+    info->tile_channels = kd ? 4 : mode_channels(c.k->mode) * c.k->ncol;
+    info->dit = kd ? 2 : 1;
     info->threads = c.k->threads;
     info->ctas_per_sm = std::max(1, occupancy_of(*st, c, has_mem != 0, g_use_tma && c.k->tma_ok));
     info->smem_bytes = (int)c.k->smem_bytes(c.gate_tables, g_use_tma && c.k->tma_ok, g_use_tma && g_use_tmem && c.k->tmem_ok);

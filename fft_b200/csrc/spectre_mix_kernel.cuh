@@ -211,9 +211,14 @@ struct Dft<16, V> {
 // what lets the stage-0 table of the 4096-point plan shrink from 30 KB to 12 KB of shared memory.
 __host__ __device__ constexpr int tw_rows(int R) { return R == 16 ? 6 : R - 1; }
 
-template <int R0, int R1, int R2, int R3, bool SUBP = false>
+// SUBP = 2 (DIT2): the tile's two element columns hold the EVEN and the ODD rows of a transform of length 2 N (same four
+// channels); the two N-point sub-spectra are combined by one decimation-in-time radix-2 butterfly in the middle pass, right
+// where the gate is applied, and split again before the inverse passes -- a 2 N-point transform at the shared-memory traffic
+// of an N-point one (n_fft = 8192 in ONE pass over HBM).
+template <int R0, int R1, int R2, int R3, int SUBP = 0>
 struct Plan {
-    static constexpr bool kSub = SUBP;
+    static constexpr bool kSub = (SUBP == 1);
+    static constexpr bool kDit = (SUBP == 2);
     static constexpr int N = R0 * R1 * R2 * R3;
     static constexpr int NS = (R3 > 1) ? 4 : ((R2 > 1) ? 3 : ((R1 > 1) ? 2 : 1));
     static_assert(NS >= 2, "at least two stages");
@@ -240,7 +245,7 @@ __host__ __device__ constexpr int tmem_box_rows(int ncol) { return 512 / ncol < 
 // ring slots of a plan: the sub-transform variant holds a full-length gate table (two half-length slots) and has room for six,
 // or for five next to its stage-0 twiddle rows (measured faster: profiles/r01d_ab_sub_twiddles.txt)
 template <class PL>
-__host__ __device__ constexpr int tmem_slots() { return PL::kSub ? (SPX_SUB_TW_SMEM ? 5 : 6) : kTmemSlotsMax; }
+__host__ __device__ constexpr int tmem_slots() { return (PL::kSub || PL::kDit) ? (SPX_SUB_TW_SMEM ? 5 : 6) : kTmemSlotsMax; }
 // register split of the TMEM variant (512 compute + 128 helper threads, 96 per thread at launch = 61440 in the CTA pool)
 #ifndef SPX_ILV
 #define SPX_ILV 1
@@ -560,6 +565,17 @@ __device__ __forceinline__ void tma_store_3d(const void *tmap, uint32_t src, int
                  "r"(row), "r"(b), "r"(src)
                  : "memory");
 }
+// rank-4 forms for the DIT2 variant: tensor [B][n][parity][C] (row = 2 n + parity), box {channels, 2, rows, 1}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const void *tmap, int c, int par, int row, int b, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+        ::"r"(dst), "l"(tmap), "r"(c), "r"(par), "r"(row), "r"(b), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const void *tmap, uint32_t src, int c, int par, int row, int b) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%1, %2, %3, %4}], [%5];" ::"l"(tmap), "r"(c),
+                 "r"(par), "r"(row), "r"(b), "r"(src)
+                 : "memory");
+}
 __device__ __forceinline__ void tma_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int PENDING>
 __device__ __forceinline__ void tma_wait_read() {
@@ -712,20 +728,20 @@ __device__ __forceinline__ GateRow<ANCH> gate_row(const MixParams &p, int b, int
     return r;
 }
 
-// gate row -> registers (all loads in flight), registers -> padded shared table
-template <int N, int NT, int GK, bool ANCH>
+// gate row -> registers (all loads in flight), registers -> padded shared table; J0 = first of the thread's entries (k = tid + j NT)
+template <int N, int NT, int GK, bool ANCH, int J0 = 0>
 __device__ __forceinline__ void gate_fetch(float2 (&gv)[GK], const GateRow<ANCH> &gr, int tid) {
 #pragma unroll
     for (int j = 0; j < GK; ++j) {
-        const int k = tid + j * NT;
+        const int k = tid + (j + J0) * NT;
         gv[j] = (k <= N / 2) ? gr.at(k) : make_float2(0.f, 0.f);
     }
 }
-template <int N, int NT, int GK>
+template <int N, int NT, int GK, int J0 = 0>
 __device__ __forceinline__ void gate_put(float2 *gs, const float2 (&gv)[GK], int tid, float inv_n) {
 #pragma unroll
     for (int j = 0; j < GK; ++j) {
-        const int k = tid + j * NT;
+        const int k = tid + (j + J0) * NT;
         if (k <= N / 2) {
             const float im = (k == 0 || k == N / 2) ? 0.f : gv[j].y * inv_n;
             gs[k + (k >> 4)] = make_float2(gv[j].x * inv_n, im);
@@ -867,12 +883,19 @@ __global__ void __launch_bounds__(NT + ((TMA_IN && NT >= kSepProducerMinThreads)
 
     constexpr int GK = (N / 2 + 1 + NT - 1) / NT;   // gate entries per thread
     constexpr bool SUB = PL::kSub;
+    constexpr bool DIT = PL::kDit;                  // columns = even / odd rows of a 2 N-point transform (see Plan)
+    constexpr int NTOT = DIT ? 2 * N : N;           // transform length the gate / memory belong to
+    constexpr int GKD = (NTOT / 2 + 1 + NT - 1) / NT;   // DIT: gate entries per thread (half spectrum of the 2 N-point transform)
+    constexpr int GKD1 = DIT ? 5 : 1;               // ... of which this many are parked in registers across the inner inverse pass,
+    constexpr int GKD2 = DIT ? GKD - GKD1 : 1;      // the rest is fetched and published right after it (register pressure)
+    static_assert(!DIT || (TMEM_IO && NCOL == 2 && MODE == MODE_QUAD && !RFFT_ONLY && !DGATE && PL::NS == 3 && PL::R(2) == 16),
+                  "DIT2 variant: TMEM-staged packed kernel with two element columns");
     constexpr int GKS = SUB ? N / NT : 1;           // sub-transform: full-length gate table, entries per thread
     static_assert(!SUB || (N % NT == 0 && MODE == MODE_QUAD && !RFFT_ONLY), "sub-transform variant: packed mix kernel only");
     // tables fetched for the NEXT tile while this one finishes (parked in registers across the inner inverse pass): one, or
     // two on the wide tiles whose 32 channels span two 16-channel gate groups
     constexpr int kEarlyGT = (!SUB && NCOL * CH >= 32) ? 2 : 1;
-    const bool gate_early = SUB || (p.gate_tables <= kEarlyGT);
+    const bool gate_early = SUB || DIT || (p.gate_tables <= kEarlyGT);
     const TIN *vbase = reinterpret_cast<const TIN *>(p.v);
     TOUT *obase = reinterpret_cast<TOUT *>(p.out);
     const int CE = p.C / CH;  // elements per row
@@ -987,23 +1010,27 @@ __global__ void __launch_bounds__(NT + ((TMA_IN && NT >= kSepProducerMinThreads)
             // path between two barriers is the helper's critical path, so no divisions there except once per tile
             int ld_left = total_boxes, ld_k = 0, ld_t = tile_of(0), ld_tb = 0, ld_tc = 0, ld_seq = 0;
             uint32_t ld_slot = 0;
+            constexpr int TCH = DIT ? CH : NCOL * CH;             // channels per tile
             if (my_tiles > 0) {
                 ld_tb = ld_t / p.tiles_per_row;
-                ld_tc = (ld_t - ld_tb * p.tiles_per_row) * NCOL * CH;
+                ld_tc = (ld_t - ld_tb * p.tiles_per_row) * TCH;
             }
             auto issue_next = [&]() {                             // load thread: next box of the stream -> next slot
                 // (no proxy fence: the slot was last touched by shared-memory READS of the helper threads, ordered by the
                 // helper barrier, or by a TMA store whose read the store thread has waited for)
                 mbar_expect_tx(bar_landed + 8 * ld_slot, SLOTB);
-                tma_load_3d(smem_u32(stg) + ld_slot * SLOTB, (DGATE && (ld_seq & 1)) ? &tmap_out : &tmap, ld_tc, ld_k * TBOXR, ld_tb,
-                            bar_landed + 8 * ld_slot);
+                if constexpr (DIT)
+                    tma_load_4d(smem_u32(stg) + ld_slot * SLOTB, &tmap, ld_tc, 0, ld_k * TBOXR, ld_tb, bar_landed + 8 * ld_slot);
+                else
+                    tma_load_3d(smem_u32(stg) + ld_slot * SLOTB, (DGATE && (ld_seq & 1)) ? &tmap_out : &tmap, ld_tc, ld_k * TBOXR, ld_tb,
+                                bar_landed + 8 * ld_slot);
                 --ld_left;
                 ld_slot = (ld_slot + 1 == kTmemSlots) ? 0 : ld_slot + 1;
                 if (++ld_k == NBOX) {
                     ld_k = 0;
                     ld_t = tile_of(++ld_seq);
                     ld_tb = ld_t / p.tiles_per_row;
-                    ld_tc = (ld_t - ld_tb * p.tiles_per_row) * NCOL * CH;
+                    ld_tc = (ld_t - ld_tb * p.tiles_per_row) * TCH;
                 }
             };
             // two duty threads in different warps so the store and the load of a step are issued side by side: kStoreLane
@@ -1046,7 +1073,7 @@ __global__ void __launch_bounds__(NT + ((TMA_IN && NT >= kSepProducerMinThreads)
 #endif
                 const int td = do_drain ? tile_of(P - 2) : 0;
                 const int tb = do_drain ? td / p.tiles_per_row : 0;
-                const int tc = do_drain ? (td - tb * p.tiles_per_row) * NCOL * CH : 0;
+                const int tc = do_drain ? (td - tb * p.tiles_per_row) * TCH : 0;
                 // cooperative prefetch target: rows of this CTA's tile P + 1 (its loads are issued one phase from now)
 #if SPX_COOP_PF
                 const TIN *pf = nullptr;
@@ -1098,7 +1125,8 @@ __global__ void __launch_bounds__(NT + ((TMA_IN && NT >= kSepProducerMinThreads)
                     const long long c3 = clock64();
 #endif
                     if (hl == kStoreLane && do_drain) {
-                        tma_store_3d(&tmap_out, smem_u32(slot), tc, k * TBOXR, tb);
+                        if constexpr (DIT) tma_store_4d(&tmap_out, smem_u32(slot), tc, 0, k * TBOXR, tb);
+                        else tma_store_3d(&tmap_out, smem_u32(slot), tc, k * TBOXR, tb);
                         tma_commit();
                         tma_wait_read<SP>();                       // the store of step - SP has left its slot
                     }
@@ -1206,7 +1234,7 @@ __global__ void __launch_bounds__(NT + ((TMA_IN && NT >= kSepProducerMinThreads)
         }
         const int b = SUB ? (brow >> p.sub_shift) : brow;        // batch row (gate / memory)
         const int qsub = SUB ? (brow & (p.sub_R - 1)) : 0;       // which interleaved sub-transform
-        const int ce0 = tcol * NCOL;                             // first element column of the tile
+        const int ce0 = DIT ? tcol : tcol * NCOL;                // first element (4-channel group) of the tile; DIT: the only one
         const int c0 = ce0 * CH;
         const int g0 = gdiv(c0);
         const bool full_tile = (ce0 + NCOL <= CE) && (p.n_in == N);
@@ -1215,7 +1243,13 @@ __global__ void __launch_bounds__(NT + ((TMA_IN && NT >= kSepProducerMinThreads)
         // ---- stage the gate tables of this tile (asynchronous copies, awaited before the barrier that follows stage 0).
         // With one table per tile this was already started while the previous tile finished (see below); else do it here.
         if constexpr (!RFFT_ONLY && !DGATE) {
-            if constexpr (SUB) {
+            if constexpr (DIT) {
+                if (seq == 0) {   // half spectrum of the 2 N-point transform: N + 1 entries in the two table slots
+                    float2 gv[GKD];
+                    gate_fetch<NTOT, NT, GKD>(gv, gate_row<ANCH>(p, b, g0, NTOT / 2 + 1), tid);
+                    gate_put<NTOT, NT, GKD>(gate_s, gv, tid, p.inv_n);
+                }
+            } else if constexpr (SUB) {
                 if (seq == 0) {
                     float2 gv[GKS];
                     gate_fetch_sub<N, NT, GKS>(gv, gate_row<ANCH>(p, b, g0, (N * p.sub_R) / 2 + 1), tid, qsub, p.sub_R);
@@ -1371,7 +1405,7 @@ __global__ void __launch_bounds__(NT + ((TMA_IN && NT >= kSepProducerMinThreads)
                     col = kIlv ? w % NCOL : w / NBF;
                     Q = kIlv ? w / NCOL : w - col * NBF;
                 }
-                if ((ce0 + col) >= CE) continue;   // column past the last channel: nothing to transform
+                if ((DIT ? ce0 : ce0 + col) >= CE) continue;   // column past the last channel: nothing to transform
                 const int e0 = Q * RL;
                 S *cb = buf + col * CS + e0 + (e0 >> 4);
                 Cx<V> x[RL];
@@ -1379,7 +1413,7 @@ __global__ void __launch_bounds__(NT + ((TMA_IN && NT >= kSepProducerMinThreads)
                 for (int m = 0; m < RL; ++m) x[m] = E::unpack(cb[m]);
                 Dft<RL, V>::run(x);
                 const int klow = klow_of<PL>(Q);
-                const int cabs = (ce0 + col) * CH;                 // first channel of this element
+                const int cabs = (DIT ? ce0 : ce0 + col) * CH;     // first channel of this element
                 if constexpr (RFFT_ONLY) {
                     // half spectrum out (spectre.py:506 / :777): bins k <= n_fft/2 of this channel
                     float2 *sp = reinterpret_cast<float2 *>(p.out) + (long long)b * p.o_sb + cabs;
@@ -1423,6 +1457,70 @@ __global__ void __launch_bounds__(NT + ((TMA_IN && NT >= kSepProducerMinThreads)
                             tn[k + (k >> 4)] = t[q];
                         }
                     }
+                    continue;
+                }
+                if constexpr (DIT) {
+                    // x[q] = S_c[k'], k' = klow + PLAST q: the N-point spectrum of the rows 2 n + c (c = col = lane parity).  The two
+                    // lanes of a pair trade halves so that lane c owns q in [8 c, 8 c + 8) of BOTH sub-spectra (32 shuffles each
+                    // way, same work on both lanes), then for each of its bins:
+                    //   X[k'] = S0 + W^k' S1,  X[k' + N] = S0 - W^k' S1          (W = exp(-2 pi i / 2N): decimation in time)
+                    //   Y = Gfull X (+ memory)                                   (Gfull[k' + N] = conj(G[N - k']), Hermitian)
+                    //   S0' = Y[k'] + Y[k' + N],  S1' = conj(W^k') (Y[k'] - Y[k' + N])
+                    static_assert(RL == 16, "DIT2 middle pass: radix-16 last stage");
+                    const bool odd = (col & 1) != 0;
+                    // component-wise register selects (a struct-valued ?: on array elements becomes a pointer select and demotes the
+                    // array to local memory)
+                    auto csel = [](bool c, const Cx<V> a, const Cx<V> b) {
+                        Cx<V> r;
+                        r.re.x = c ? a.re.x : b.re.x; r.re.y = c ? a.re.y : b.re.y;
+                        r.im.x = c ? a.im.x : b.im.x; r.im.y = c ? a.im.y : b.im.y;
+                        return r;
+                    };
+                    auto shx = [](const Cx<V> &a) {
+                        Cx<V> r;
+                        r.re.x = __shfl_xor_sync(0xffffffffu, a.re.x, 1); r.re.y = __shfl_xor_sync(0xffffffffu, a.re.y, 1);
+                        r.im.x = __shfl_xor_sync(0xffffffffu, a.im.x, 1); r.im.y = __shfl_xor_sync(0xffffffffu, a.im.y, 1);
+                        return r;
+                    };
+                    float wbs, wbc;                                    // W^klow = exp(-i pi klow / N)
+                    sincospif(-(float)klow * (1.0f / (float)N), &wbs, &wbc);
+                    const float2 *gs = gate_s;
+                    // one bin pair at a time (trade, combine, gate, split, trade back): only 16 + ~6 packed values are ever live
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const Cx<V> recv = shx(csel(odd, x[j], x[j + 8]));
+                        const Cx<V> s0 = csel(odd, recv, x[j]);
+                        const Cx<V> s1 = csel(odd, x[j + 8], recv);
+                        // W^(PLAST q) = W_32^q, q = j + 8 odd: W_32^(j + 8) = -i W_32^j
+                        constexpr float c32[8] = {1.f, 0.98078528040323044913f, 0.92387953251128675613f, 0.83146961230254523708f,
+                                                  0.70710678118654752440f, 0.55557023301960222474f, 0.38268343236508977173f,
+                                                  0.19509032201612826785f};
+                        constexpr float s32[8] = {0.f, -0.19509032201612826785f, -0.38268343236508977173f, -0.55557023301960222474f,
+                                                  -0.70710678118654752440f, -0.83146961230254523708f, -0.92387953251128675613f,
+                                                  -0.98078528040323044913f};
+                        float wr = wbc * c32[j] - wbs * s32[j], wi = wbc * s32[j] + wbs * c32[j];
+                        if (odd) { const float t_ = wr; wr = wi; wi = -t_; }
+                        const int kp = klow + PLAST * (j + (odd ? 8 : 0));       // k' in [0, N)
+                        const int km = N - kp;                                   // mirror partner of bin k' + N, in [1, N]
+                        const Cx<V> t = cmul(s1, wr, wi);
+                        Cx<V> lo = cadd(s0, t), hi = csub(s0, t);
+                        const float2 glo = gs[kp + (kp >> 4)], ghi = gs[km + (km >> 4)];
+                        lo = cmul(lo, glo.x, glo.y);
+                        hi = cmulc(hi, ghi.x, ghi.y);
+                        if (HAS_MEM) {
+                            const float sg = (kp == 0) ? 0.f : p.inv_n;          // imag of DC (lo) and of Nyquist (hi) ignored
+                            mem_add(lo, p.mem + (long long)kp * p.mem_stride + cabs, p.inv_n, sg, MODE);
+                            mem_add(hi, p.mem + (long long)km * p.mem_stride + cabs, p.inv_n, -sg, MODE);
+                        }
+                        const Cx<V> r0 = cadd(lo, hi);                           // S0'[q]
+                        const Cx<V> r1 = cmulc(csub(lo, hi), wr, wi);            // S1'[q]
+                        const Cx<V> back = shx(csel(odd, r0, r1));
+                        x[j] = cswap(csel(odd, back, r0));
+                        x[j + 8] = cswap(csel(odd, r1, back));
+                    }
+                    Dft<RL, V>::run(x);
+#pragma unroll
+                    for (int m = 0; m < RL; ++m) cb[m] = E::pack(cswap(x[m]));
                     continue;
                 }
                 const float2 *gs = gate_s + (p.gate_tables == 1 ? 0 : (gdiv(cabs) - g0) * GS);
@@ -1504,14 +1602,16 @@ __global__ void __launch_bounds__(NT + ((TMA_IN && NT >= kSepProducerMinThreads)
 
         // the gate table is free again: start fetching the next tile's gate row, park it in registers
         // across the inner inverse passes, and publish it before the last pass
-        float2 gnext[SUB ? GKS : (SPX_GATE_ASYNC ? 1 : GK)];
+        float2 gnext[SUB ? GKS : (DIT ? GKD1 : (SPX_GATE_ASYNC ? 1 : GK))];
         [[maybe_unused]] float2 gnext2[kEarlyGT == 2 ? GK : 1];   // second table of a wide tile
         const bool fetch_next = gate_early && tile_next_ < p.num_tiles && !partner_next;   // the partner tile reuses the table
         int nq = 0;
         if (fetch_next) {
             const int nrow = nrow_;
-            const int ng = gdiv(ncol_ * NCOL * CH);
-            if constexpr (SUB) {
+            const int ng = gdiv(ncol_ * (DIT ? CH : NCOL * CH));
+            if constexpr (DIT) {
+                gate_fetch<NTOT, NT, GKD1>(gnext, gate_row<ANCH>(p, nrow, ng, NTOT / 2 + 1), tid);
+            } else if constexpr (SUB) {
                 nq = nrow & (p.sub_R - 1);
                 gate_fetch_sub<N, NT, GKS>(gnext, gate_row<ANCH>(p, nrow >> p.sub_shift, ng, (N * p.sub_R) / 2 + 1), tid, nq, p.sub_R);
             } else {
@@ -1528,7 +1628,12 @@ __global__ void __launch_bounds__(NT + ((TMA_IN && NT >= kSepProducerMinThreads)
         if constexpr (NS > 3) { inv_inner_pass<PL, MODE, NCOL, NT, 2, kIlv>(buf, tw, p.tw, tid); cta_sync<NT, SEP>(); }
         if constexpr (NS > 2) { inv_inner_pass<PL, MODE, NCOL, NT, 1, kIlv>(buf, tw, p.tw, tid); cta_sync<NT, SEP>(); }
         if (fetch_next) {
-            if constexpr (SUB) {
+            if constexpr (DIT) {
+                gate_put<NTOT, NT, GKD1>(gate_s, gnext, tid, p.inv_n);
+                float2 g2[GKD2];
+                gate_fetch<NTOT, NT, GKD2, ANCH, GKD1>(g2, gate_row<ANCH>(p, nrow_, gdiv(ncol_ * CH), NTOT / 2 + 1), tid);
+                gate_put<NTOT, NT, GKD2, GKD1>(gate_s, g2, tid, p.inv_n);
+            } else if constexpr (SUB) {
                 gate_put_sub<N, NT, GKS>(gate_s, gnext, tid, nq, p.sub_R, p.inv_n);
             } else {
 #if SPX_GATE_ASYNC

@@ -29,6 +29,7 @@ struct KernelEntry {
     int tmem_ok;   // 1: a TMEM-staged variant exists (tile I/O parked in tensor memory by a helper warpgroup)
     int sub;       // 1: sub-transform variant of the long-context two-pass path (complex input, strided gate gather)
     int anch_ok;   // 1: variants that evaluate the gate from anchors inside the gate staging exist (packed mode)
+    int dit;       // 2: DIT2 variant -- the two tile columns are the even / odd rows of a transform of length 2 * n_fft
     // forward half only (half spectrum out); MODE_REAL variants only, else nullptr
     cudaError_t (*launch_rfft)(const MixParams &p, int grid, cudaStream_t st);
     // gate gradient: TMEM-staged packed variants only, else nullptr; tmap_v / tmap_dy describe V and dY
@@ -55,14 +56,19 @@ struct Launcher {
             &spectre_mix_kernel<PL, MODE, NCOL, NT, MINB, TIO, TIO, HAS_MEM, false, (TMA && kTma), (TMA && TMEM && kTmem), (ANCH && kAnch)>);
     }
     static const void *pick(bool has_mem, bool tma, bool tmem = false, bool anch = false) {
-        if (anch && kAnch) {
-            if (tma && tmem && kTmem) return has_mem ? fn<true, true, true, true>() : fn<false, true, true, true>();
-            if (tma && kTma) return has_mem ? fn<true, true, false, true>() : fn<false, true, false, true>();
-            return has_mem ? fn<true, false, false, true>() : fn<false, false, false, true>();
+        if constexpr (PL::kDit) {   // DIT2: TMEM-staged variants only
+            if (anch) return has_mem ? fn<true, true, true, true>() : fn<false, true, true, true>();
+            return has_mem ? fn<true, true, true>() : fn<false, true, true>();
+        } else {
+            if (anch && kAnch) {
+                if (tma && tmem && kTmem) return has_mem ? fn<true, true, true, true>() : fn<false, true, true, true>();
+                if (tma && kTma) return has_mem ? fn<true, true, false, true>() : fn<false, true, false, true>();
+                return has_mem ? fn<true, false, false, true>() : fn<false, false, false, true>();
+            }
+            if (tma && tmem && kTmem) return has_mem ? fn<true, true, true>() : fn<false, true, true>();
+            if (tma && kTma) return has_mem ? fn<true, true, false>() : fn<false, true, false>();
+            return has_mem ? fn<true, false, false>() : fn<false, false, false>();
         }
-        if (tma && tmem && kTmem) return has_mem ? fn<true, true, true>() : fn<false, true, true>();
-        if (tma && kTma) return has_mem ? fn<true, true, false>() : fn<false, true, false>();
-        return has_mem ? fn<true, false, false>() : fn<false, false, false>();
     }
     static cudaError_t launch(const MixParams &p, int grid, bool has_mem, const CUtensorMap *tmap, const CUtensorMap *tmap_out,
                               bool tmem, cudaStream_t st) {
@@ -91,7 +97,7 @@ struct Launcher {
         return cudaLaunchKernel(f, dim3(grid), dim3(NT), args, sm, st);
     }
     static cudaError_t launch_dgate(const MixParams &p, int grid, const CUtensorMap *tmap_v, const CUtensorMap *tmap_dy, cudaStream_t st) {
-        if constexpr (kTmem && PL::NS == 3 && !PL::kSub && PL::R(2) == 16) {
+        if constexpr (kTmem && PL::NS == 3 && !PL::kSub && !PL::kDit && PL::R(2) == 16) {
             const size_t sm = smem_bytes(1, true, true);
             const void *f = reinterpret_cast<const void *>(
                 &spectre_mix_kernel<PL, MODE, NCOL, NT, MINB, TIO, TIO, false, false, true, true, false, true>);
@@ -105,7 +111,7 @@ struct Launcher {
             return cudaErrorNotSupported;
         }
     }
-    static constexpr bool kDgate = kTmem && PL::NS == 3 && !PL::kSub && PL::R(2) == 16;
+    static constexpr bool kDgate = kTmem && PL::NS == 3 && !PL::kSub && !PL::kDit && PL::R(2) == 16;
     static int occupancy(int gate_tables, bool has_mem, bool tma, bool tmem) {
         const size_t sm = smem_bytes(gate_tables, tma, tmem);
         const void *f = pick(has_mem, tma, tmem);
@@ -143,7 +149,7 @@ struct RfftPtr<PL, MODE_REAL, NCOL, NT, MINB, TIO> {
             &::spx::Launcher<::spx::Plan<R0, R1, R2, R3>, MODE, NCOL, NT, MINB, TIO>::occupancy,              \
             ::spx::Launcher<::spx::Plan<R0, R1, R2, R3>, MODE, NCOL, NT, MINB, TIO>::kTma ? 1 : 0,            \
             ::spx::Launcher<::spx::Plan<R0, R1, R2, R3>, MODE, NCOL, NT, MINB, TIO>::kTmem ? 1 : 0, 0,        \
-            ::spx::Launcher<::spx::Plan<R0, R1, R2, R3>, MODE, NCOL, NT, MINB, TIO>::kAnch ? 1 : 0,           \
+            ::spx::Launcher<::spx::Plan<R0, R1, R2, R3>, MODE, NCOL, NT, MINB, TIO>::kAnch ? 1 : 0, 0,        \
             ::spx::RfftPtr<::spx::Plan<R0, R1, R2, R3>, MODE, NCOL, NT, MINB, TIO>::get(),                    \
             ::spx::Launcher<::spx::Plan<R0, R1, R2, R3>, MODE, NCOL, NT, MINB, TIO>::kDgate                   \
                 ? &::spx::Launcher<::spx::Plan<R0, R1, R2, R3>, MODE, NCOL, NT, MINB, TIO>::launch_dgate : nullptr \
@@ -159,8 +165,22 @@ struct RfftPtr<PL, MODE_REAL, NCOL, NT, MINB, TIO> {
             &::spx::Launcher<::spx::Plan<R0, R1, R2, R3, true>, MODE, NCOL, NT, MINB, TIO>::occupancy,        \
             ::spx::Launcher<::spx::Plan<R0, R1, R2, R3, true>, MODE, NCOL, NT, MINB, TIO>::kTma ? 1 : 0,      \
             ::spx::Launcher<::spx::Plan<R0, R1, R2, R3, true>, MODE, NCOL, NT, MINB, TIO>::kTmem ? 1 : 0, 1,  \
-            ::spx::Launcher<::spx::Plan<R0, R1, R2, R3, true>, MODE, NCOL, NT, MINB, TIO>::kAnch ? 1 : 0,     \
+            ::spx::Launcher<::spx::Plan<R0, R1, R2, R3, true>, MODE, NCOL, NT, MINB, TIO>::kAnch ? 1 : 0, 0,  \
             nullptr, nullptr                                                                                           \
+    }
+
+#define SPX_ENTRY_DIT(R0, R1, R2, R3, MODE, NCOL, NT, MINB, TIO, IOCODE)                                     \
+    {                                                                                                         \
+        (R0) * (R1) * (R2) * (R3), {R0, R1, R2, R3}, MODE, IOCODE, NCOL, NT, MINB,                            \
+            ::spx::Plan<R0, R1, R2, R3, 2>::TWN,                                                              \
+            &::spx::Launcher<::spx::Plan<R0, R1, R2, R3, 2>, MODE, NCOL, NT, MINB, TIO>::smem_bytes,          \
+            ::spx::Smem<::spx::Plan<R0, R1, R2, R3, 2>, MODE, NCOL>::OUT_BOX_ROWS, ::spx::tmem_box_rows(NCOL), \
+            &::spx::Launcher<::spx::Plan<R0, R1, R2, R3, 2>, MODE, NCOL, NT, MINB, TIO>::launch,              \
+            &::spx::Launcher<::spx::Plan<R0, R1, R2, R3, 2>, MODE, NCOL, NT, MINB, TIO>::occupancy,           \
+            ::spx::Launcher<::spx::Plan<R0, R1, R2, R3, 2>, MODE, NCOL, NT, MINB, TIO>::kTma ? 1 : 0,         \
+            ::spx::Launcher<::spx::Plan<R0, R1, R2, R3, 2>, MODE, NCOL, NT, MINB, TIO>::kTmem ? 1 : 0, 0,     \
+            ::spx::Launcher<::spx::Plan<R0, R1, R2, R3, 2>, MODE, NCOL, NT, MINB, TIO>::kAnch ? 1 : 0, 2,     \
+            nullptr, nullptr                                                                                  \
     }
 
 // one table per instantiation file

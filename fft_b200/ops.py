@@ -455,5 +455,5 @@ def plan_info(B: int, N: int, n_fft: int, C: int, group_width: int, dtype: torch
         "n_fft": info.n_fft, "radix": [r for r in info.radix if r > 1], "tile_channels": info.tile_channels,
         "threads": info.threads, "ctas_per_sm": info.ctas_per_sm, "smem_bytes": info.smem_bytes,
         "grid": info.grid, "launches": info.launches, "algorithmic_bytes": info.algorithmic_bytes,
-        "workspace_bytes": info.workspace_bytes,
+        "workspace_bytes": info.workspace_bytes, "dit": info.dit,
     }

@@ -185,6 +185,9 @@ typedef struct spectre_mix_plan_info {
     int launches;          /* kernel launches per call */
     int64_t algorithmic_bytes; /* V + out + gate (+ mem) bytes of the call */
     int64_t workspace_bytes;   /* = spectre_mix_workspace_bytes(...) */
+    int dit;               /* 2: the transform runs as two interleaved half-length sub-transforms (even / odd rows) combined by a
+                              radix-2 butterfly inside the kernel's middle pass (n_fft = 8192 fp32); radix[] then describes the
+                              sub-transform.  1 otherwise */
 } spectre_mix_plan_info;
 
 int spectre_mix_plan(int v_dtype, int out_dtype, int has_mem, int B, int N, int n_fft, int C,
@@ -203,8 +206,9 @@ int spectre_mix_set_tma(int enable);
  * exists (n_fft = 4096 fp32).  For experiments only. */
 int spectre_mix_set_tmem(int enable);
 
-/* Long transforms (n_fft > 4096): 0 = single-kernel variants only, 1 = automatic (default: the TMEM-staged single kernel where
- * one exists -- n_fft = 8192 fp32 -- else the three-launch path around a workspace), 2 = the three-launch path wherever possible. */
+/* Long transforms (n_fft > 4096): 0 = single-kernel variants only, 1 = automatic (default: a single TMEM-staged kernel where
+ * one exists -- n_fft = 8192 fp32 -- else the three-launch path around a workspace), 2 = the three-launch path wherever possible.
+ * spectre_mix_set_sched bit 5 (32) switches the DIT2 variant of n_fft = 8192 off (experiments: falls back to Plan<16,2,16,16>). */
 int spectre_mix_set_two_pass(int enable);
 
 /* Warp stagger before the warp-local passes: 0 = off; code > 0: hold back half of the warps by `code` nanoseconds;

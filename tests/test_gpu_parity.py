@@ -841,7 +841,9 @@ def test_long_context_two_pass_and_single_kernel_agree(fb, oracle, dev):
     assert fb.plan_info(4, 16384, 16384, 768, 16)["launches"] == 3
     # n_fft = 8192 fp32: the TMEM-staged single kernel is the default (one pass over HBM, no workspace); bf16 keeps three launches
     info = fb.plan_info(4, 8192, 8192, 768, 16)
-    assert info["launches"] == 1 and info["workspace_bytes"] == 0 and info["radix"] == [16, 2, 16, 16] and info["tile_channels"] == 4
+    assert info["launches"] == 1 and info["workspace_bytes"] == 0 and info["tile_channels"] == 4
+    assert info["dit"] == 2 and info["radix"] == [16, 16, 16]          # even / odd rows, radix-2 combine in the middle pass
+    assert fb.plan_info(4, 8191, 8192, 768, 16)["radix"] == [16, 2, 16, 16]   # odd row count: the plain single kernel
     assert fb.plan_info(4, 8192, 8192, 768, 16, torch.bfloat16)["launches"] == 3
     Vb = torch.randn(1, 16384, 32, generator=torch.Generator().manual_seed(60)).to(torch.bfloat16)
     gate = torch.randn(1, 2, 8193, dtype=torch.cfloat, generator=torch.Generator().manual_seed(61))
