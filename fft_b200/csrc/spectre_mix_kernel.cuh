@@ -259,8 +259,16 @@ __host__ __device__ constexpr int tmem_slots() { return (PL::kSub || PL::kDit) ?
 #ifndef SPX_COOP_PF
 #define SPX_COOP_PF 0
 #endif
+#ifndef SPX_HELPER_GATE
+#define SPX_HELPER_GATE 0   // TMEM kernels with a materialised gate and one table per tile: the helper warpgroup stages the gate rows.
+                            // Correct, but the helper has ~6 % slack per tile: 10.8 us per tile against 9.2 (profiles/r03a_ab_helper_gate.txt)
+#endif
 #ifndef SPX_GATE_ASYNC
-#define SPX_GATE_ASYNC 0
+#define SPX_GATE_ASYNC 0   // next tile's gate row by LDGSTS straight into the table: 0 never, 1 wherever possible, 2 kernels with both tensor-memory exchanges
+#endif
+#ifndef SPX_TMEMX
+#define SPX_TMEMX 0   // 4096-class TMEM kernels, exchanges through tensor memory: bit 0 stage 1 -> middle pass, bit 1 middle pass -> inverse stage 1.
+                      // Correct and 31 % less shared-memory traffic, but no faster (the kernel is not bound there): see DESIGN 3.9
 #endif
 #ifndef SPX_TMEM_COMPUTE_REGS
 #define SPX_TMEM_COMPUTE_REGS 112
@@ -430,7 +438,7 @@ struct Smem {
     static constexpr int STG_ROWS = STG_MB * PL::L(0);                       // rows per staging round
     static constexpr int OUT_BOX_ROWS = cmin_(STG_ROWS, 256);                // rows per TMA store
     __host__ __device__ static constexpr size_t stg_bytes(size_t row_bytes) { return (size_t)STG_ROWS * row_bytes; }
-    static constexpr size_t bar_bytes = 128;
+    static constexpr size_t bar_bytes = 256;
     __host__ __device__ static constexpr size_t base_bytes(int gate_tables) { return data_bytes + tw_bytes + gate_bytes_one * (size_t)gate_tables; }
     // TMEM variant: ring of kTmemSlots + kTmemStoreSlots TMA boxes (256 rows each) instead of the staging buffers
     static constexpr size_t bytes(int gate_tables, bool tma = false, size_t row_bytes = 0, bool tmem = false) {
@@ -605,6 +613,91 @@ __device__ __forceinline__ void tmem_st4(uint32_t a, float r0, float r1, float r
 }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// ---- warp-local 16 x 16 transposes THROUGH tensor memory (no shared-memory traffic; tools/microbench/tmem_xchg.cu)
+// A .32x32b store puts register column c of lane s at (lane s, column c); a .16x256b load at lane half hh hands thread t the
+// columns 8 i + 2 (t % 4) + {0, 1} of lanes t / 4 + 8 v + 16 hh.  One store + two loads therefore move the top two lane bits of
+// the source into the register index and two register-index bits into the low two lane bits, shifting the other lane bits up by
+// two.  Two such steps turn the stage-1 layout (lane = 2 u + col, register q) into the middle-pass layout (lane = 16 col + q,
+// register u); the twin with the shapes swapped is the exact inverse.  Each step runs as four 16-column quarters, so a warp needs
+// 16 columns of tensor memory.  LDTM / STTM run on their own pipe: measured 1400 cycles per 128 KB exchange and SM, and almost
+// fully hidden behind shared-memory traffic, against 2050 cycles of LSU time for the shared-memory exchange.
+__device__ __forceinline__ void tmem_st_32x16(uint32_t a, const float (&r)[16]) {
+#define SPX_U(i) "r"(__float_as_uint(r[i]))
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(a),
+                 SPX_U(0), SPX_U(1), SPX_U(2), SPX_U(3), SPX_U(4), SPX_U(5), SPX_U(6), SPX_U(7), SPX_U(8), SPX_U(9), SPX_U(10), SPX_U(11),
+                 SPX_U(12), SPX_U(13), SPX_U(14), SPX_U(15) : "memory");
+}
+__device__ __forceinline__ void tmem_st_16x256x2(uint32_t a, const float (&r)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.16x256b.x2.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(a), SPX_U(0), SPX_U(1), SPX_U(2),
+                 SPX_U(3), SPX_U(4), SPX_U(5), SPX_U(6), SPX_U(7) : "memory");
+#undef SPX_U
+}
+__device__ __forceinline__ void tmem_ld_32x16(uint32_t a, float (&r)[16]) {
+    uint32_t u[16];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]), "=r"(u[8]), "=r"(u[9]),
+                   "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15]) : "r"(a) : "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) r[i] = __uint_as_float(u[i]);
+}
+__device__ __forceinline__ void tmem_ld_16x256x2(uint32_t a, float (&r)[8]) {
+    uint32_t u[8];
+    asm volatile("tcgen05.ld.sync.aligned.16x256b.x2.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]) : "r"(a) : "memory");
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r[i] = __uint_as_float(u[i]);
+}
+// word f of a packed element: (re.x, re.y, im.x, im.y) -- the two halves of a packed-fp32x2 register pair stay adjacent columns
+__device__ __forceinline__ float &cx_word(Cx<float2> &c, int f) { return f == 0 ? c.re.x : (f == 1 ? c.re.y : (f == 2 ? c.im.x : c.im.y)); }
+// HI: exchange element-index bits 3:2 (quarters = bits 1:0); else bits 1:0 (quarters = bits 3:2)
+template <bool HI>
+__device__ __forceinline__ void tmem_xchg_step_fwd(Cx<float2> (&x)[16], uint32_t tx) {
+#pragma unroll
+    for (int h = 0; h < 4; ++h) {
+        float s[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) s[j] = cx_word(x[HI ? 4 * ((j >> 1) & 3) + h : 4 * h + ((j >> 1) & 3)], (j & 1) + 2 * (j >> 3));
+        tmem_st_32x16(tx, s);
+        tmem_wait_st();
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+            float r[8];   // r[4 i + 2 v + f0]: repetition i = word bit 1, v = source lane + 8, f0 = word bit 0
+            tmem_ld_16x256x2(tx + ((uint32_t)(16 * hh) << 16), r);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) cx_word(x[HI ? 4 * (2 * hh + ((j >> 1) & 1)) + h : 4 * h + 2 * hh + ((j >> 1) & 1)], (j & 1) + 2 * (j >> 2)) = r[j];
+        }
+        tmem_wait_ld();
+    }
+}
+template <bool HI>
+__device__ __forceinline__ void tmem_xchg_step_inv(Cx<float2> (&x)[16], uint32_t tx) {
+#pragma unroll
+    for (int h = 0; h < 4; ++h) {
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+            float r[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) r[j] = cx_word(x[HI ? 4 * (2 * hh + ((j >> 1) & 1)) + h : 4 * h + 2 * hh + ((j >> 1) & 1)], (j & 1) + 2 * (j >> 2));
+            tmem_st_16x256x2(tx + ((uint32_t)(16 * hh) << 16), r);
+        }
+        tmem_wait_st();
+        float s[16];
+        tmem_ld_32x16(tx, s);
+        tmem_wait_ld();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) cx_word(x[HI ? 4 * ((j >> 1) & 3) + h : 4 * h + ((j >> 1) & 3)], (j & 1) + 2 * (j >> 3)) = s[j];
+    }
+}
+// stage-1 layout -> middle-pass layout and back (see above)
+__device__ __forceinline__ void tmem_xchg_fwd(Cx<float2> (&x)[16], uint32_t tx) { tmem_xchg_step_fwd<true>(x, tx); tmem_xchg_step_fwd<false>(x, tx); }
+__device__ __forceinline__ void tmem_xchg_inv(Cx<float2> (&x)[16], uint32_t tx) { tmem_xchg_step_inv<false>(x, tx); tmem_xchg_step_inv<true>(x, tx); }
+template <class T> __device__ __forceinline__ void tmem_xchg_fwd(T &, uint32_t) {}   // other element types: never instantiated for use
+template <class T> __device__ __forceinline__ void tmem_xchg_inv(T &, uint32_t) {}
+template <bool FIRST, class A, class B>
+__device__ __forceinline__ auto &pick_ref(A &a, B &b) {
+    if constexpr (FIRST) return a; else return b;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void helper_bar() { asm volatile("bar.sync 2, 128;" ::: "memory"); }
@@ -773,6 +866,22 @@ __device__ __forceinline__ void gate_scale_own(float2 *gs, int tid, float inv_n)
     }
 }
 
+// the same two steps for the helper warpgroup (128 threads at 32 registers: rolled loops, nothing hoisted)
+template <int N>
+__device__ __forceinline__ void gate_copy_async_rolled(float2 *gs, const float2 *gp, int t) {
+#pragma unroll 1
+    for (int k = t; k <= N / 2; k += 128)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(gs + k + (k >> 4))), "l"(gp + k) : "memory");
+}
+template <int N>
+__device__ __forceinline__ void gate_scale_own_rolled(float2 *gs, int t, float inv_n) {
+#pragma unroll 1
+    for (int k = t; k <= N / 2; k += 128) {
+        const float2 g = gs[k + (k >> 4)];
+        gs[k + (k >> 4)] = make_float2(g.x * inv_n, (k == 0 || k == N / 2) ? 0.f : g.y * inv_n);
+    }
+}
+
 // barrier over the NT compute threads only (the TMA producer warp of the TMA variant never joins it)
 template <int NT, bool NAMED>
 __device__ __forceinline__ void cta_sync() {
@@ -824,7 +933,7 @@ __global__ void __launch_bounds__(NT + ((TMA_IN && NT >= kSepProducerMinThreads)
     constexpr int ITEMS0 = NCOL * L0;                       // stage-0 butterflies per tile
     constexpr int ITERS0 = (ITEMS0 + NT - 1) / NT;          // per thread
     static_assert(!TMA_IN || (MODE == MODE_QUAD && !RFFT_ONLY), "TMA path is built for the packed mix kernel");
-    static_assert(!ANCH || (!RFFT_ONLY && !SPX_GATE_ASYNC), "in-kernel gate generation: mix kernels, register-staged gate rows");
+    static_assert(!ANCH || !RFFT_ONLY, "in-kernel gate generation: mix kernels");
     // DGATE (backward of the mix w.r.t. the gate): every tile is visited twice -- first with V's rows (forward
     // transform, packed spectrum stashed in this thread's own tensor-memory lane: the TMEM-OUT half is free, nothing is
     // drained), then with dY's rows (tensor map 2), whose spectrum is multiplied by the conjugate of the stash, reduced over the
@@ -844,6 +953,25 @@ __global__ void __launch_bounds__(NT + ((TMA_IN && NT >= kSepProducerMinThreads)
     // inner passes and the middle pass map (column, butterfly) -> thread with the two element columns on adjacent lanes: gate and
     // twiddle reads of a lane pair coincide (one wavefront instead of two); the exchanges stay inside a warp
     constexpr bool kIlv = (SPX_ILV != 0) && TMEM_IO && kWarpLocal && NS == 3 && NCOL == 2 && MODE == MODE_QUAD;
+    // stage 1, the middle pass and inverse stage 1 in registers, linked by two warp-local transposes through tensor memory
+    // (tmem_xchg_fwd / _inv): one thread = one stage-1 butterfly = one middle-pass item.  The 16 columns a warp needs are cells of
+    // TMEM-IN that belong to the LAST kTmemXBoxes input boxes: free once every warp has pulled its tile (the barrier after stage
+    // 0), refilled by the helper only after every warp has reported its second exchange done (barrier +120).
+    constexpr bool kTmemX = ((SPX_TMEMX & 1) != 0) && kIlv && !DGATE && !PL::kDit && !PL::kSub && !RFFT_ONLY && (NCOL * (N / 16) == NT) && (NT == 512);
+    constexpr int kTmemXBoxes = 4;
+    // the way back (middle pass -> inverse stage 1) through tensor memory as well.  Off by default: it keeps the 16 elements live
+    // across the next tile's gate prefetch, and ptxas then spills the freshly loaded gate row (a wait for DRAM in every tile);
+    // with the row sent by LDGSTS instead (SPX_GATE_ASYNC) the tile start pays.  Measured 10.0 / 11.1 us per tile against 9.2.
+    constexpr bool kTmemXI = kTmemX && ((SPX_TMEMX & 2) != 0);
+    // The next tile's gate row goes into the table by asynchronous 8-byte copies instead of through registers.  With kTmemX the
+    // registers that would park the row across inverse stage 1 do not exist (the transform's 16 elements stay live from stage 1
+    // to the last inverse pass): ptxas spilled the freshly loaded row to local memory, i.e. waited for DRAM right there.
+    constexpr bool kGateAsync = (SPX_GATE_ASYNC == 1 || (SPX_GATE_ASYNC == 2 && kTmemXI)) && !ANCH && !PL::kSub && !PL::kDit && !DGATE && !RFFT_ONLY;
+    // Experiment (off): the helper warpgroup stages the gate rows (LDGSTS into the table at the start of the phase that follows the
+    // tile's parking, its own entries rescaled two steps later, published on barrier +128).  Without any gate staging the compute
+    // warps run 9.0 instead of 9.2 us per tile (profiles/r02x_ab_nogate.txt), but the helper's loop is nearly as long as the
+    // compute warps' and every wait added to it stalls the load stream: 10.4 - 10.8 us per tile with the row staged there.
+    constexpr bool kHelperGate = (SPX_HELPER_GATE != 0) && TMEM_IO && !ANCH && !PL::kSub && !PL::kDit && !DGATE && !RFFT_ONLY && !kGateAsync;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     S *buf = reinterpret_cast<S *>(smem_raw);
     float2 *tw = reinterpret_cast<float2 *>(smem_raw + SM::data_bytes);
@@ -896,6 +1024,7 @@ __global__ void __launch_bounds__(NT + ((TMA_IN && NT >= kSepProducerMinThreads)
     // two on the wide tiles whose 32 channels span two 16-channel gate groups
     constexpr int kEarlyGT = (!SUB && NCOL * CH >= 32) ? 2 : 1;
     const bool gate_early = SUB || DIT || (p.gate_tables <= kEarlyGT);
+    const bool hgate = kHelperGate && p.gate_tables == 1;   // the helper warpgroup stages the gate rows (see kHelperGate)
     const TIN *vbase = reinterpret_cast<const TIN *>(p.v);
     TOUT *obase = reinterpret_cast<TOUT *>(p.out);
     const int CE = p.C / CH;  // elements per row
@@ -956,6 +1085,8 @@ __global__ void __launch_bounds__(NT + ((TMA_IN && NT >= kSepProducerMinThreads)
     // barriers:  +0 tile parked in TMEM-IN (helper)   +8 TMEM-IN consumed (NW warps)   +16 results parked in TMEM-OUT (NW warps)
     //            +24 TMEM-OUT drained (helper)   +32.. ring slot landed (TMA tx, kTmemSlots of them, < +96)   +96 TMEM base address
     //            +104 twiddle table landed   +112 last inverse pass has read the buffer (NW warps, split barrier)
+    //            +120 both tensor-memory exchanges of the tile done (NW warps): the last input boxes may be parked (kTmemX)
+    //            +128 gate row of the tile the compute warps work on is in the table (helper; kHelperGate)
     // ring (the staging area): kTmemSlots slots of one 256-row TMA box each, used for loads while parking and for
     // stores while draining
     [[maybe_unused]] uint32_t tmem_base = 0;
@@ -971,6 +1102,8 @@ __global__ void __launch_bounds__(NT + ((TMA_IN && NT >= kSepProducerMinThreads)
             mbar_init(bar_out_full, NW);
             mbar_init(bar_out_free, 1);
             mbar_init(bar + 112, NW);                                  // inverse stage-0 read done (split barrier, sched bit 1)
+            mbar_init(bar + 120, NW);                                  // both tensor-memory exchanges of the tile done (kTmemX)
+            mbar_init(bar + 128, 1);                                   // gate row of the tile in work staged (helper; kHelperGate)
 #pragma unroll
             for (int i = 0; i < kTmemSlots; ++i) mbar_init(bar_landed + 8 * i, 1);
         }
@@ -985,6 +1118,7 @@ __global__ void __launch_bounds__(NT + ((TMA_IN && NT >= kSepProducerMinThreads)
             const uint32_t tq = tmem_base + ((uint32_t)(hl & ~31) << 16);
             constexpr int NBOX = N / TBOXR;                       // TMA boxes per tile
             constexpr int GPB = TBOXR * NCOL / 128;               // 128-element groups per box
+            [[maybe_unused]] constexpr int kGateStep = NBOX >= 3 ? 2 : NBOX - 1;   // kHelperGate: step after which the staged gate row is published
 #ifndef SPX_TMEM_SP
 #define SPX_TMEM_SP 1
 #endif
@@ -1064,7 +1198,20 @@ __global__ void __launch_bounds__(NT + ((TMA_IN && NT >= kSepProducerMinThreads)
                 long long c_land = 0, c_move = 0, c_bar = 0, c_tma = 0;
                 if (tl_on) tl[0] = globaltimer_ns();
 #endif
-                if (do_park && P >= 1) mbar_wait(bar_in_free, (P - 1) & 1);    // compute warps pulled tile P-1 out of TMEM-IN
+                // kHelperGate: while the compute warps work on tile P - 1 the helper stages that tile's gate row.  They have pulled the tile
+                // (this wait), so they are past the barrier that ends inverse stage 1 of tile P - 2: nobody reads the table any more.  The
+                // copies (LDGSTS, no registers) land under the first steps; after step kGateStep the helper rescales its own entries
+                // and publishes the table on barrier +128, which the compute warps await before their middle pass (~ 3 us from here)
+                const bool do_gate = kHelperGate && hgate && P >= 1 && P <= my_tiles;
+                if ((do_park || do_gate) && P >= 1) mbar_wait(bar_in_free, (P - 1) & 1);    // compute warps pulled tile P-1 out of TMEM-IN
+                if constexpr (kHelperGate) {
+                    if (do_gate) {
+                        const int tg = tile_of(P - 1);
+                        const int gb = tg / p.tiles_per_row, gc = (tg - gb * p.tiles_per_row) * TCH;
+                        const int gg = p.gw_shift >= 0 ? (gc >> p.gw_shift) : gc / p.group_width;
+                        gate_copy_async_rolled<N>(gate_s, p.gate + ((long long)gb * p.NG + gg) * (N / 2 + 1), hl);
+                    }
+                }
                 if (do_drain) mbar_wait(bar_out_full, (P - 2) & 1);            // results of tile P-2 sit in TMEM-OUT
                 tc_fence_after();
                 if (p.prefetch == 1 && hl == kLoadLane && P + 2 < my_tiles) prefetch_tile(tile_of(P + 2));
@@ -1098,6 +1245,13 @@ __global__ void __launch_bounds__(NT + ((TMA_IN && NT >= kSepProducerMinThreads)
                     long long c0 = clock64(), c1 = c0;
 #endif
                     if (do_park) {
+                        if constexpr (kTmemX) {
+                            // the cells of the last input boxes are the compute warps' exchange columns while they work on tile P - 1
+                            if (k == NBOX - kTmemXBoxes && P >= 1) {
+                                mbar_wait(bar + 120, (P - 1) & 1);
+                                tc_fence_after();
+                            }
+                        }
                         mbar_wait(bar_landed + 8 * sl, (landed_par >> sl) & 1);
                         landed_par ^= 1u << sl;
 #if SPX_HELPER_TL
@@ -1117,6 +1271,12 @@ __global__ void __launch_bounds__(NT + ((TMA_IN && NT >= kSepProducerMinThreads)
                         for (int g = 0; g < GPB; ++g) slot[g * 128 + hl] = Lin<MODE, TOUT>::put(v[g]);
                         fence_proxy_async();
                     }
+                    if constexpr (kHelperGate) {
+                        if (do_gate && k == kGateStep) {           // own copies have landed: 1/n_fft, imag(DC) = imag(Nyquist) = 0
+                            cp_async_wait_all();
+                            gate_scale_own_rolled<N>(gate_s, hl, p.inv_n);
+                        }
+                    }
 #if SPX_HELPER_TL
                     const long long c2 = clock64();
 #endif
@@ -1124,6 +1284,9 @@ __global__ void __launch_bounds__(NT + ((TMA_IN && NT >= kSepProducerMinThreads)
 #if SPX_HELPER_TL
                     const long long c3 = clock64();
 #endif
+                    if constexpr (kHelperGate) {
+                        if (do_gate && k == kGateStep && hl == 0) mbar_arrive(bar + 128);
+                    }
                     if (hl == kStoreLane && do_drain) {
                         if constexpr (DIT) tma_store_4d(&tmap_out, smem_u32(slot), tc, 0, k * TBOXR, tb);
                         else tma_store_3d(&tmap_out, smem_u32(slot), tc, k * TBOXR, tb);
@@ -1255,17 +1418,19 @@ __global__ void __launch_bounds__(NT + ((TMA_IN && NT >= kSepProducerMinThreads)
                     gate_fetch_sub<N, NT, GKS>(gv, gate_row<ANCH>(p, b, g0, (N * p.sub_R) / 2 + 1), tid, qsub, p.sub_R);
                     gate_put_sub<N, NT, GKS>(gate_s, gv, tid, qsub, p.sub_R, p.inv_n);
                 }
+            } else if (hgate) {
+                // the helper warpgroup staged this tile's row before it announced the tile
             } else if (!gate_early || seq == 0) {
                 for (int t = 0; t < p.gate_tables; ++t) {
                     const int g = g0 + t;
                     if (g < p.NG) {
-#if SPX_GATE_ASYNC
-                        gate_copy_async<N, NT, GK>(gate_s + t * GS, p.gate + ((long long)b * p.NG + g) * (N / 2 + 1), tid);
-#else
-                        float2 gv[GK];
-                        gate_fetch<N, NT, GK>(gv, gate_row<ANCH>(p, b, g, N / 2 + 1), tid);
-                        gate_put<N, NT, GK>(gate_s + t * GS, gv, tid, p.inv_n);
-#endif
+                        if constexpr (kGateAsync) {
+                            gate_copy_async<N, NT, GK>(gate_s + t * GS, p.gate + ((long long)b * p.NG + g) * (N / 2 + 1), tid);
+                        } else {
+                            float2 gv[GK];
+                            gate_fetch<N, NT, GK>(gv, gate_row<ANCH>(p, b, g, N / 2 + 1), tid);
+                            gate_put<N, NT, GK>(gate_s + t * GS, gv, tid, p.inv_n);
+                        }
                     }
                 }
             }
@@ -1368,7 +1533,7 @@ __global__ void __launch_bounds__(NT + ((TMA_IN && NT >= kSepProducerMinThreads)
                 }
             }
         }
-        if constexpr (!RFFT_ONLY && !SUB && SPX_GATE_ASYNC) {
+        if constexpr (kGateAsync) {
             // this thread's share of the gate tables has landed: rescale it in place before the barrier publishes it
             cp_async_wait_all();
             for (int t = 0; t < p.gate_tables; ++t)
@@ -1384,10 +1549,33 @@ __global__ void __launch_bounds__(NT + ((TMA_IN && NT >= kSepProducerMinThreads)
         // The exchange between stage NS-2 and the middle pass is a 16x16 transpose among the 16 threads that share
         // (column, leading digits): with consecutive butterflies on consecutive lanes those threads are one half-warp,
         // in this pass and in the middle pass alike, so __syncwarp() orders it and warps run on unsynchronised.
+        // kTmemX: stage 1 stays in registers (xk), is transposed through tensor memory and feeds the middle pass directly
+        [[maybe_unused]] Cx<V> xk[kTmemX ? 16 : 1];
+        [[maybe_unused]] uint32_t tmx = 0;           // this warp's 16 exchange columns: TMEM-IN cells of the last four input boxes
+        [[maybe_unused]] S *cb1 = nullptr;           // stage-1 butterfly (column tid % 2, Q = warp, u = lane / 2): its 16 buffer slots
+        if constexpr (kTmemX) {
+            static_assert(PL::R(1) == 16 && PL::L(1) == 16 && RL == 16 && NCOL == 2, "tensor-memory exchange: 16 x 16 x 16 plan, two element columns");
+            const int col1 = tid & 1, bf1 = tid >> 1, e1 = (bf1 >> 4) * 256 + (bf1 & 15);
+            cb1 = buf + col1 * CS + e1 + (e1 >> 4);
+            tmx = tmem_base + ((uint32_t)(32 * ((tid >> 5) & 3)) << 16) + (uint32_t)(TCOLS - 16 * kTmemXBoxes + 16 * (tid >> 7));
+#pragma unroll
+            for (int m = 0; m < 16; ++m) xk[m] = E::unpack(cb1[m * 16 + m]);
+            Dft<16, V>::run(xk);
+            apply_twiddles<PL, 1, V>(xk, tw, p.tw, bf1 & 15);
+            tmem_xchg_fwd(xk, tmx);                  // (every warp has pulled its tile out of TMEM-IN: the barrier after stage 0)
+            if constexpr (!kTmemXI) {
+                tc_fence_before();
+                __syncwarp();
+                if ((tid & 31) == 0) mbar_arrive(bar + 120);   // the helper may park the next tile's last boxes over the exchange columns
+            }
+        } else
         if constexpr (NS > 2) { fwd_inner_pass<PL, MODE, NCOL, NT, 1, kIlv>(buf, tw, p.tw, tid); if constexpr (NS == 3 && (kWarpLocal || kWarpLocalN)) __syncwarp(); else cta_sync<NT, SEP>(); }
         if constexpr (NS > 3) { fwd_inner_pass<PL, MODE, NCOL, NT, 2, kIlv>(buf, tw, p.tw, tid); if constexpr (kWarpLocal) __syncwarp(); else cta_sync<NT, SEP>(); }
 
         SPX_MARK(3)
+        if constexpr (kHelperGate) {
+            if (hgate) mbar_wait(bar + 128, tile_it & 1);   // the helper warpgroup has staged this tile's gate row
+        }
         // ---- middle pass: last forward butterfly -> gate (+memory) -> first inverse butterfly
         {
             constexpr int NBF = N / RL, ITEMS = NCOL * NBF;
@@ -1401,16 +1589,23 @@ __global__ void __launch_bounds__(NT + ((TMA_IN && NT >= kSepProducerMinThreads)
                     col = tid / NB1;
                     const int bf1 = tid - col * NB1, Qf = bf1 / RL, u1 = bf1 - Qf * RL;
                     Q = 16 * Qf + IPT * u1 + jj;
+                } else if constexpr (kTmemX) {
+                    // after the exchange: lane = 16 col + q1, register = u of stage 1; the warp is the leading digit
+                    col = (tid >> 4) & 1;
+                    Q = 16 * (tid >> 5) + (tid & 15);
                 } else {
                     col = kIlv ? w % NCOL : w / NBF;
                     Q = kIlv ? w / NCOL : w - col * NBF;
                 }
                 if ((DIT ? ce0 : ce0 + col) >= CE) continue;   // column past the last channel: nothing to transform
                 const int e0 = Q * RL;
-                S *cb = buf + col * CS + e0 + (e0 >> 4);
-                Cx<V> x[RL];
+                [[maybe_unused]] S *cb = buf + col * CS + e0 + (e0 >> 4);
+                [[maybe_unused]] Cx<V> xl[kTmemX ? 1 : RL];
+                Cx<V> (&x)[RL] = pick_ref<kTmemX>(xk, xl);
+                if constexpr (!kTmemX) {
 #pragma unroll
-                for (int m = 0; m < RL; ++m) x[m] = E::unpack(cb[m]);
+                    for (int m = 0; m < RL; ++m) x[m] = E::unpack(cb[m]);
+                }
                 Dft<RL, V>::run(x);
                 const int klow = klow_of<PL>(Q);
                 const int cabs = (DIT ? ce0 : ce0 + col) * CH;     // first channel of this element
@@ -1563,8 +1758,10 @@ __global__ void __launch_bounds__(NT + ((TMA_IN && NT >= kSepProducerMinThreads)
                     x[q] = cswap(x[q]);
                 }
                 Dft<RL, V>::run(x);
+                if constexpr (!kTmemXI) {
 #pragma unroll
-                for (int m = 0; m < RL; ++m) cb[m] = E::pack(cswap(x[m]));
+                    for (int m = 0; m < RL; ++m) cb[m] = E::pack(cswap(x[m]));
+                }
             }
         }
         if constexpr (DGATE) {
@@ -1600,11 +1797,26 @@ __global__ void __launch_bounds__(NT + ((TMA_IN && NT >= kSepProducerMinThreads)
         SPX_MARK(4)
         if constexpr (RFFT_ONLY) continue;
 
+        if constexpr (kTmemXI) {
+            // back to the stage-1 layout; the middle pass left (im, re)-swapped data, exactly what inverse stage 1 works on.
+            // BEFORE the gate prefetch below: tcgen05.wait::st is a fence that also waits for the thread's global loads in flight
+            tmem_xchg_inv(xk, tmx);
+            tc_fence_before();
+            __syncwarp();
+            if ((tid & 31) == 0) mbar_arrive(bar + 120);   // the helper may park the next tile's last boxes over the exchange columns
+#if defined(SPX_DIAG_X) && SPX_DIAG_X == 1
+            SPX_MARK(5)
+#endif
+        }
         // the gate table is free again: start fetching the next tile's gate row, park it in registers
         // across the inner inverse passes, and publish it before the last pass
-        float2 gnext[SUB ? GKS : (DIT ? GKD1 : (SPX_GATE_ASYNC ? 1 : GK))];
+        float2 gnext[SUB ? GKS : (DIT ? GKD1 : (kGateAsync ? 1 : GK))];
         [[maybe_unused]] float2 gnext2[kEarlyGT == 2 ? GK : 1];   // second table of a wide tile
-        const bool fetch_next = gate_early && tile_next_ < p.num_tiles && !partner_next;   // the partner tile reuses the table
+#ifdef SPX_DIAG_NOGATE   // timing experiment only (wrong results): the gate table is never refreshed
+        const bool fetch_next = false;
+#else
+        const bool fetch_next = gate_early && !hgate && tile_next_ < p.num_tiles && !partner_next;   // the partner tile reuses the table
+#endif
         int nq = 0;
         if (fetch_next) {
             const int nrow = nrow_;
@@ -1615,17 +1827,30 @@ __global__ void __launch_bounds__(NT + ((TMA_IN && NT >= kSepProducerMinThreads)
                 nq = nrow & (p.sub_R - 1);
                 gate_fetch_sub<N, NT, GKS>(gnext, gate_row<ANCH>(p, nrow >> p.sub_shift, ng, (N * p.sub_R) / 2 + 1), tid, nq, p.sub_R);
             } else {
-#if !SPX_GATE_ASYNC
-                gate_fetch<N, NT, GK>(gnext, gate_row<ANCH>(p, nrow, ng, N / 2 + 1), tid);
-                if constexpr (kEarlyGT == 2) {
-                    if (p.gate_tables == 2 && ng + 1 < p.NG) gate_fetch<N, NT, GK>(gnext2, gate_row<ANCH>(p, nrow, ng + 1, N / 2 + 1), tid);
+                if constexpr (!kGateAsync) {
+                    gate_fetch<N, NT, GK>(gnext, gate_row<ANCH>(p, nrow, ng, N / 2 + 1), tid);
+                    if constexpr (kEarlyGT == 2) {
+                        if (p.gate_tables == 2 && ng + 1 < p.NG) gate_fetch<N, NT, GK>(gnext2, gate_row<ANCH>(p, nrow, ng + 1, N / 2 + 1), tid);
+                    }
                 }
-#endif
             }
         }
 
         // ---- inverse stages NS-2 .. 1: smem -> twiddle -> butterfly -> smem (in place)
         if constexpr (NS > 3) { inv_inner_pass<PL, MODE, NCOL, NT, 2, kIlv>(buf, tw, p.tw, tid); cta_sync<NT, SEP>(); }
+        if constexpr (kTmemXI) {
+            apply_twiddles<PL, 1, V>(xk, tw, p.tw, (tid >> 1) & 15);
+            Dft<16, V>::run(xk);
+#pragma unroll
+            for (int m = 0; m < 16; ++m) cb1[m * 16 + m] = E::pack(cswap(xk[m]));
+#if defined(SPX_DIAG_X) && SPX_DIAG_X == 2
+            SPX_MARK(5)
+#endif
+            cta_sync<NT, SEP>();
+#if defined(SPX_DIAG_X) && SPX_DIAG_X == 2
+            SPX_MARK(6)
+#endif
+        } else
         if constexpr (NS > 2) { inv_inner_pass<PL, MODE, NCOL, NT, 1, kIlv>(buf, tw, p.tw, tid); cta_sync<NT, SEP>(); }
         if (fetch_next) {
             if constexpr (DIT) {
@@ -1636,20 +1861,23 @@ __global__ void __launch_bounds__(NT + ((TMA_IN && NT >= kSepProducerMinThreads)
             } else if constexpr (SUB) {
                 gate_put_sub<N, NT, GKS>(gate_s, gnext, tid, nq, p.sub_R, p.inv_n);
             } else {
-#if SPX_GATE_ASYNC
-                // every warp is past the middle pass: the next tile's gate row may stream into the table
-                const int nrow = nrow_;
-                const int ng = gdiv(ncol_ * NCOL * CH);
-                gate_copy_async<N, NT, GK>(gate_s, p.gate + ((long long)nrow * p.NG + ng) * (N / 2 + 1), tid);
-#else
-                gate_put<N, NT, GK>(gate_s, gnext, tid, p.inv_n);
-                if constexpr (kEarlyGT == 2) {
-                    if (p.gate_tables == 2 && gdiv(ncol_ * NCOL * CH) + 1 < p.NG) gate_put<N, NT, GK>(gate_s + GS, gnext2, tid, p.inv_n);
+                if constexpr (kGateAsync) {
+                    // every warp is past the middle pass: the next tile's gate row may stream into the table (kEarlyGT == 1 here:
+                    // kGateAsync kernels have 8-channel tiles, one table)
+                    const int nrow = nrow_;
+                    const int ng = gdiv(ncol_ * NCOL * CH);
+                    gate_copy_async<N, NT, GK>(gate_s, p.gate + ((long long)nrow * p.NG + ng) * (N / 2 + 1), tid);
+                } else {
+                    gate_put<N, NT, GK>(gate_s, gnext, tid, p.inv_n);
+                    if constexpr (kEarlyGT == 2) {
+                        if (p.gate_tables == 2 && gdiv(ncol_ * NCOL * CH) + 1 < p.NG) gate_put<N, NT, GK>(gate_s + GS, gnext2, tid, p.inv_n);
+                    }
                 }
-#endif
             }
         }
+#ifndef SPX_DIAG_X
         SPX_MARK(5)
+#endif
         if ((TMEM_IO || (p.sched & 64)) && (p.sched & 1)) {
             // sched bits 8..11: step of this second stagger in quarters of the first one's (0 = same step)
             const int q4 = (p.sched >> 8) & 15;
@@ -1700,7 +1928,9 @@ __global__ void __launch_bounds__(NT + ((TMA_IN && NT >= kSepProducerMinThreads)
                     Dft<R0, V>::run(x0[it]);
                 }
             }
+#if !(defined(SPX_DIAG_X) && SPX_DIAG_X == 2)
             SPX_MARK(6)
+#endif
             if constexpr (TMEM_IO) {
                 // park the results in TMEM-OUT (same lane / column-group geometry as the input side); the helper
                 // warpgroup drains them to HBM while this CTA already transforms the next tile

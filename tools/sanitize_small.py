@@ -26,7 +26,10 @@ def case(B, N, n_fft, C, dg, dt=torch.float32, mem=False):
 
 for args in [(2, 64, 64, 16, 4), (2, 1000, 1024, 32, 16), (1, 2048, 2048, 32, 8), (3, 4096, 4096, 32, 16), (2, 4000, 4096, 24, 8),
              (2, 4096, 4096, 32, 16, torch.bfloat16), (1, 8192, 8192, 32, 16), (1, 16384, 16384, 16, 16), (2, 4096, 4096, 12, 6),
-             (2, 4096, 4096, 9, 3), (2, 4096, 4096, 32, 16, torch.float32, True)]:
+             (2, 4096, 4096, 9, 3), (2, 4096, 4096, 32, 16, torch.float32, True),
+             # wide-row TMEM variants (batch large enough to select them), DIT2 at 8192 (even rows) and its odd-row fallback
+             (40, 1024, 1024, 800, 16), (24, 2000, 2048, 784, 16, torch.float32, True), (2, 8190, 8192, 32, 16, torch.float32, True),
+             (1, 8191, 8192, 32, 16)]:
     case(*args)
 # fused gate generator
 B, n_fft, G, dg = 2, 4096, 4, 16

@@ -15,6 +15,8 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from fft_b200 import _lib  # noqa: E402
 
+if os.environ.get("SPX_ALT"):
+    _lib.LIB_PATH = _lib.LIB_PATH.replace("libspectre_mix.so", "libspectre_mix_%s.so" % os.environ["SPX_ALT"])
 lib = _lib.load()
 import pynvml  # noqa: E402
 
