@@ -438,6 +438,7 @@ int mix_dit(DeviceState &st, const KernelEntry &k, const void *v, int dtype, lon
     p.prefetch = 0;
     p.skew_ns = g_skew_ns.load(std::memory_order_relaxed);
     p.sched = g_sched.load(std::memory_order_relaxed) & ~(16 | 8 | 4);
+    p.timeline = g_timeline.load(std::memory_order_relaxed);
     p.sub_R = 1;
     p.gw_shift = ilog2_exact(group_width);
     alignas(64) CUtensorMap tmap, tmap_out;

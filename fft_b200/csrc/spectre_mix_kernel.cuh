@@ -263,6 +263,9 @@ __host__ __device__ constexpr int tmem_slots() { return (PL::kSub || PL::kDit) ?
 #define SPX_HELPER_GATE 0   // TMEM kernels with a materialised gate and one table per tile: the helper warpgroup stages the gate rows.
                             // Correct, but the helper has ~6 % slack per tile: 10.8 us per tile against 9.2 (profiles/r03a_ab_helper_gate.txt)
 #endif
+#ifndef SPX_DIT_ASYNC
+#define SPX_DIT_ASYNC 1   // DIT2 kernels with a materialised gate: rows go into the table by LDGSTS, unscaled (1/n applied in the middle pass)
+#endif
 #ifndef SPX_GATE_ASYNC
 #define SPX_GATE_ASYNC 0   // next tile's gate row by LDGSTS straight into the table: 0 never, 1 wherever possible, 2 kernels with both tensor-memory exchanges
 #endif
@@ -971,6 +974,11 @@ __global__ void __launch_bounds__(NT + ((TMA_IN && NT >= kSepProducerMinThreads)
     // tile's parking, its own entries rescaled two steps later, published on barrier +128).  Without any gate staging the compute
     // warps run 9.0 instead of 9.2 us per tile (profiles/r02x_ab_nogate.txt), but the helper's loop is nearly as long as the
     // compute warps' and every wait added to it stalls the load stream: 10.4 - 10.8 us per tile with the row staged there.
+    // DIT2 (n_fft = 8192): the gate row is 33 KB, nine entries per thread.  Parked in registers across inverse stage 1 it gets
+    // spilled by ptxas right behind its loads (a wait for DRAM in every tile); so the row goes into the table by asynchronous
+    // 8-byte copies after the barrier that ends inverse stage 1, raw, and the middle pass applies 1/n and the imag(DC) =
+    // imag(Nyquist) = 0 rule when it reads an entry (four scalar products per bin pair).
+    constexpr bool kDitAsync = (SPX_DIT_ASYNC != 0) && PL::kDit && !ANCH && !RFFT_ONLY && !DGATE;
     constexpr bool kHelperGate = (SPX_HELPER_GATE != 0) && TMEM_IO && !ANCH && !PL::kSub && !PL::kDit && !DGATE && !RFFT_ONLY && !kGateAsync;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     S *buf = reinterpret_cast<S *>(smem_raw);
@@ -1408,9 +1416,13 @@ __global__ void __launch_bounds__(NT + ((TMA_IN && NT >= kSepProducerMinThreads)
         if constexpr (!RFFT_ONLY && !DGATE) {
             if constexpr (DIT) {
                 if (seq == 0) {   // half spectrum of the 2 N-point transform: N + 1 entries in the two table slots
-                    float2 gv[GKD];
-                    gate_fetch<NTOT, NT, GKD>(gv, gate_row<ANCH>(p, b, g0, NTOT / 2 + 1), tid);
-                    gate_put<NTOT, NT, GKD>(gate_s, gv, tid, p.inv_n);
+                    if constexpr (kDitAsync) {
+                        gate_copy_async<NTOT, NT, GKD>(gate_s, p.gate + ((long long)b * p.NG + g0) * (NTOT / 2 + 1), tid);
+                    } else {
+                        float2 gv[GKD];
+                        gate_fetch<NTOT, NT, GKD>(gv, gate_row<ANCH>(p, b, g0, NTOT / 2 + 1), tid);
+                        gate_put<NTOT, NT, GKD>(gate_s, gv, tid, p.inv_n);
+                    }
                 }
             } else if constexpr (SUB) {
                 if (seq == 0) {
@@ -1533,6 +1545,7 @@ __global__ void __launch_bounds__(NT + ((TMA_IN && NT >= kSepProducerMinThreads)
                 }
             }
         }
+        if constexpr (kDitAsync) cp_async_wait_all();   // this thread's share of the (raw) gate row has landed; the barrier publishes it
         if constexpr (kGateAsync) {
             // this thread's share of the gate tables has landed: rescale it in place before the barrier publishes it
             cp_async_wait_all();
@@ -1699,7 +1712,12 @@ __global__ void __launch_bounds__(NT + ((TMA_IN && NT >= kSepProducerMinThreads)
                         const int km = N - kp;                                   // mirror partner of bin k' + N, in [1, N]
                         const Cx<V> t = cmul(s1, wr, wi);
                         Cx<V> lo = cadd(s0, t), hi = csub(s0, t);
-                        const float2 glo = gs[kp + (kp >> 4)], ghi = gs[km + (km >> 4)];
+                        float2 glo = gs[kp + (kp >> 4)], ghi = gs[km + (km >> 4)];
+                        if constexpr (kDitAsync) {   // raw row in the table: 1/n here; imag of DC (kp = 0) and of Nyquist (km = N) ignored
+                            glo.x *= p.inv_n; ghi.x *= p.inv_n;
+                            glo.y = (kp == 0) ? 0.f : glo.y * p.inv_n;
+                            ghi.y = (kp == 0) ? 0.f : ghi.y * p.inv_n;
+                        }
                         lo = cmul(lo, glo.x, glo.y);
                         hi = cmulc(hi, ghi.x, ghi.y);
                         if (HAS_MEM) {
@@ -1821,7 +1839,9 @@ __global__ void __launch_bounds__(NT + ((TMA_IN && NT >= kSepProducerMinThreads)
         if (fetch_next) {
             const int nrow = nrow_;
             const int ng = gdiv(ncol_ * (DIT ? CH : NCOL * CH));
-            if constexpr (DIT) {
+            if constexpr (kDitAsync) {
+                // nothing to park: the row is copied straight into the table after the barrier below
+            } else if constexpr (DIT) {
                 gate_fetch<NTOT, NT, GKD1>(gnext, gate_row<ANCH>(p, nrow, ng, NTOT / 2 + 1), tid);
             } else if constexpr (SUB) {
                 nq = nrow & (p.sub_R - 1);
@@ -1852,12 +1872,15 @@ __global__ void __launch_bounds__(NT + ((TMA_IN && NT >= kSepProducerMinThreads)
 #endif
         } else
         if constexpr (NS > 2) { inv_inner_pass<PL, MODE, NCOL, NT, 1, kIlv>(buf, tw, p.tw, tid); cta_sync<NT, SEP>(); }
+        // DIT2: the second part of the next tile's gate row is fetched here and parked across the last inverse pass (its registers are
+        // free now: nothing else is live between the barrier above and that pass's loads), published after its butterflies
+        [[maybe_unused]] float2 g2[DIT ? GKD2 : 1];
         if (fetch_next) {
-            if constexpr (DIT) {
+            if constexpr (kDitAsync) {
+                gate_copy_async<NTOT, NT, GKD>(gate_s, p.gate + ((long long)nrow_ * p.NG + gdiv(ncol_ * CH)) * (NTOT / 2 + 1), tid);
+            } else if constexpr (DIT) {
                 gate_put<NTOT, NT, GKD1>(gate_s, gnext, tid, p.inv_n);
-                float2 g2[GKD2];
                 gate_fetch<NTOT, NT, GKD2, ANCH, GKD1>(g2, gate_row<ANCH>(p, nrow_, gdiv(ncol_ * CH), NTOT / 2 + 1), tid);
-                gate_put<NTOT, NT, GKD2, GKD1>(gate_s, g2, tid, p.inv_n);
             } else if constexpr (SUB) {
                 gate_put_sub<N, NT, GKS>(gate_s, gnext, tid, nq, p.sub_R, p.inv_n);
             } else {
@@ -1926,6 +1949,13 @@ __global__ void __launch_bounds__(NT + ((TMA_IN && NT >= kSepProducerMinThreads)
                 if (ITEMS0 % NT == 0 || w < ITEMS0) {
                     apply_twiddles<PL, 0, V>(x0[it], tw, p.tw, u);
                     Dft<R0, V>::run(x0[it]);
+                }
+            }
+            if constexpr (DIT) {
+                // (every warp is past the middle pass since the barrier that ended inverse stage 1; the next one reads the table
+                // after the barrier that ends the next tile's stage 0)
+                if constexpr (!kDitAsync) {
+                    if (fetch_next) gate_put<NTOT, NT, GKD2, GKD1>(gate_s, g2, tid, p.inv_n);
                 }
             }
 #if !(defined(SPX_DIAG_X) && SPX_DIAG_X == 2)
