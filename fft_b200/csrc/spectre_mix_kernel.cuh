@@ -259,6 +259,9 @@ __host__ __device__ constexpr int tmem_slots() { return (PL::kSub || PL::kDit) ?
 #ifndef SPX_COOP_PF
 #define SPX_COOP_PF 0
 #endif
+#ifndef SPX_LAZY_STORE_WAIT
+#define SPX_LAZY_STORE_WAIT 0   // helper: await the previous TMA store's read just before the NEXT step's barrier instead of right after the commit (measured: no change, profiles/r03h_ab_lazy_store_wait.txt)
+#endif
 #ifndef SPX_HELPER_GATE
 #define SPX_HELPER_GATE 0   // TMEM kernels with a materialised gate and one table per tile: the helper warpgroup stages the gate rows.
                             // Correct, but the helper has ~6 % slack per tile: 10.8 us per tile against 9.2 (profiles/r03a_ab_helper_gate.txt)
@@ -1285,6 +1288,12 @@ __global__ void __launch_bounds__(NT + ((TMA_IN && NT >= kSepProducerMinThreads)
                             gate_scale_own_rolled<N>(gate_s, hl, p.inv_n);
                         }
                     }
+#if SPX_LAZY_STORE_WAIT && SPX_SPLIT_DUTY
+                    // the load issued after this barrier reuses the slot of the store of step - 2: that store's read must be over.
+                    // Waiting here, behind this step's data movement, instead of right after the commit keeps the elected thread off
+                    // the critical path (all but the latest SP committed stores have been read)
+                    if (hl == kStoreLane) tma_wait_read<SP>();
+#endif
 #if SPX_HELPER_TL
                     const long long c2 = clock64();
 #endif
@@ -1299,7 +1308,9 @@ __global__ void __launch_bounds__(NT + ((TMA_IN && NT >= kSepProducerMinThreads)
                         if constexpr (DIT) tma_store_4d(&tmap_out, smem_u32(slot), tc, 0, k * TBOXR, tb);
                         else tma_store_3d(&tmap_out, smem_u32(slot), tc, k * TBOXR, tb);
                         tma_commit();
+#if !(SPX_LAZY_STORE_WAIT && SPX_SPLIT_DUTY)
                         tma_wait_read<SP>();                       // the store of step - SP has left its slot
+#endif
                     }
                     if (hl == kLoadLane && ld_left > 0) issue_next();   // into a slot whose store is known to have been read
 #if SPX_HELPER_TL
