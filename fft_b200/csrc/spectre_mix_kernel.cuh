@@ -1833,9 +1833,6 @@ __global__ void __launch_bounds__(NT + ((TMA_IN && NT >= kSepProducerMinThreads)
             tc_fence_before();
             __syncwarp();
             if ((tid & 31) == 0) mbar_arrive(bar + 120);   // the helper may park the next tile's last boxes over the exchange columns
-#if defined(SPX_DIAG_X) && SPX_DIAG_X == 1
-            SPX_MARK(5)
-#endif
         }
         // the gate table is free again: start fetching the next tile's gate row, park it in registers
         // across the inner inverse passes, and publish it before the last pass
@@ -1874,13 +1871,7 @@ __global__ void __launch_bounds__(NT + ((TMA_IN && NT >= kSepProducerMinThreads)
             Dft<16, V>::run(xk);
 #pragma unroll
             for (int m = 0; m < 16; ++m) cb1[m * 16 + m] = E::pack(cswap(xk[m]));
-#if defined(SPX_DIAG_X) && SPX_DIAG_X == 2
-            SPX_MARK(5)
-#endif
             cta_sync<NT, SEP>();
-#if defined(SPX_DIAG_X) && SPX_DIAG_X == 2
-            SPX_MARK(6)
-#endif
         } else
         if constexpr (NS > 2) { inv_inner_pass<PL, MODE, NCOL, NT, 1, kIlv>(buf, tw, p.tw, tid); cta_sync<NT, SEP>(); }
         // DIT2: the second part of the next tile's gate row is fetched here and parked across the last inverse pass (its registers are
@@ -1909,9 +1900,7 @@ __global__ void __launch_bounds__(NT + ((TMA_IN && NT >= kSepProducerMinThreads)
                 }
             }
         }
-#ifndef SPX_DIAG_X
         SPX_MARK(5)
-#endif
         if ((TMEM_IO || (p.sched & 64)) && (p.sched & 1)) {
             // sched bits 8..11: step of this second stagger in quarters of the first one's (0 = same step)
             const int q4 = (p.sched >> 8) & 15;
@@ -1969,9 +1958,7 @@ __global__ void __launch_bounds__(NT + ((TMA_IN && NT >= kSepProducerMinThreads)
                     if (fetch_next) gate_put<NTOT, NT, GKD2, GKD1>(gate_s, g2, tid, p.inv_n);
                 }
             }
-#if !(defined(SPX_DIAG_X) && SPX_DIAG_X == 2)
             SPX_MARK(6)
-#endif
             if constexpr (TMEM_IO) {
                 // park the results in TMEM-OUT (same lane / column-group geometry as the input side); the helper
                 // warpgroup drains them to HBM while this CTA already transforms the next tile
