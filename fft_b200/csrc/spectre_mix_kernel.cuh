@@ -270,7 +270,8 @@ __host__ __device__ constexpr int tmem_slots() { return (PL::kSub || PL::kDit) ?
 #define SPX_DIT_ASYNC 1   // DIT2 kernels with a materialised gate: rows go into the table by LDGSTS, unscaled (1/n applied in the middle pass)
 #endif
 #ifndef SPX_GATE_ASYNC
-#define SPX_GATE_ASYNC 0   // next tile's gate row by LDGSTS straight into the table: 0 never, 1 wherever possible, 2 kernels with both tensor-memory exchanges
+#define SPX_GATE_ASYNC 0   // next tile's gate row by LDGSTS straight into the table: 0 never, 1 wherever possible, 2 kernels with both tensor-memory
+                           // exchanges, 3 TMEM kernels with 8- / 16-channel tiles and the row left RAW (1/n applied in the middle pass)
 #endif
 #ifndef SPX_TMEMX
 #define SPX_TMEMX 0   // 4096-class TMEM kernels, exchanges through tensor memory: bit 0 stage 1 -> middle pass, bit 1 middle pass -> inverse stage 1.
@@ -972,7 +973,11 @@ __global__ void __launch_bounds__(NT + ((TMA_IN && NT >= kSepProducerMinThreads)
     // The next tile's gate row goes into the table by asynchronous 8-byte copies instead of through registers.  With kTmemX the
     // registers that would park the row across inverse stage 1 do not exist (the transform's 16 elements stay live from stage 1
     // to the last inverse pass): ptxas spilled the freshly loaded row to local memory, i.e. waited for DRAM right there.
-    constexpr bool kGateAsync = (SPX_GATE_ASYNC == 1 || (SPX_GATE_ASYNC == 2 && kTmemXI)) && !ANCH && !PL::kSub && !PL::kDit && !DGATE && !RFFT_ONLY;
+    constexpr bool kGateAsync = (SPX_GATE_ASYNC == 1 || SPX_GATE_ASYNC == 3 || (SPX_GATE_ASYNC == 2 && kTmemXI)) && !ANCH && !PL::kSub &&
+                                !PL::kDit && !DGATE && !RFFT_ONLY && (SPX_GATE_ASYNC != 3 || (TMEM_IO && NCOL * CH < 32));
+    // mode 3: the table keeps the RAW row (no rescaling pass); the middle pass applies 1/n and the imag(DC) = imag(Nyquist) = 0
+    // rule where it reads an entry, as the DIT2 kernel does
+    constexpr bool kGateRaw = kGateAsync && (SPX_GATE_ASYNC == 3);
     // Experiment (off): the helper warpgroup stages the gate rows (LDGSTS into the table at the start of the phase that follows the
     // tile's parking, its own entries rescaled two steps later, published on barrier +128).  Without any gate staging the compute
     // warps run 9.0 instead of 9.2 us per tile (profiles/r02x_ab_nogate.txt), but the helper's loop is nearly as long as the
@@ -1560,8 +1565,10 @@ __global__ void __launch_bounds__(NT + ((TMA_IN && NT >= kSepProducerMinThreads)
         if constexpr (kGateAsync) {
             // this thread's share of the gate tables has landed: rescale it in place before the barrier publishes it
             cp_async_wait_all();
-            for (int t = 0; t < p.gate_tables; ++t)
-                if (g0 + t < p.NG) gate_scale_own<N, NT, GK>(gate_s + t * GS, tid, p.inv_n);
+            if constexpr (!kGateRaw) {
+                for (int t = 0; t < p.gate_tables; ++t)
+                    if (g0 + t < p.NG) gate_scale_own<N, NT, GK>(gate_s + t * GS, tid, p.inv_n);
+            }
         }
         cta_sync<NT, SEP>();
         SPX_MARK(2)
@@ -1778,7 +1785,11 @@ __global__ void __launch_bounds__(NT + ((TMA_IN && NT >= kSepProducerMinThreads)
                         k = nk - PLAST * q;
                         kp = k + (k >> 4);
                     }
-                    const float2 g = gs[kp];
+                    float2 g = gs[kp];
+                    if constexpr (kGateRaw) {
+                        g.x *= p.inv_n;
+                        g.y = ((q == 0 || q == RL / 2) && klow == 0) ? 0.f : g.y * p.inv_n;
+                    }
                     x[q] = lower ? cmul(x[q], g.x, g.y) : cmulc(x[q], g.x, g.y);
                     if (HAS_MEM) {
                         const float sgn = ((q == 0 || q == RL / 2) && klow == 0) ? 0.f : (lower ? p.inv_n : -p.inv_n);
