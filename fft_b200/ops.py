@@ -6,6 +6,7 @@ and the stream; the arithmetic is the sm_100a kernel in ``fft_b200/csrc``.
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes
 from typing import Optional
 
@@ -59,7 +60,7 @@ def _mix_impl(V: torch.Tensor, gate: torch.Tensor, memory: Optional[torch.Tensor
     if out.numel() == 0:
         return out
     lib = _lib.load()
-    with torch.cuda.device(V.device):
+    with (contextlib.nullcontext() if V.device.index == torch.cuda.current_device() else torch.cuda.device(V.device)):
         # scratch of the long-context path (n_fft > 4096) comes from torch's caching allocator: owned by this call's
         # stream, safe with side streams and under CUDA-graph capture (the kernel never allocates)
         ws_bytes = lib.spectre_mix_workspace_bytes(_DT[V.dtype], B, N, n_fft, C, group_width)
@@ -179,6 +180,12 @@ def spectral_mix(V: torch.Tensor, gate: torch.Tensor, memory: Optional[torch.Ten
     returns (B, min(N, n_fft), C) in V's dtype.
     """
     _require_cuda(V, "V")
+    needs_grad = torch.is_grad_enabled() and (V.requires_grad or gate.requires_grad or
+                                               (memory is not None and memory.requires_grad))
+    if not needs_grad and not torch.compiler.is_compiling():
+        # inference: straight to the C ABI -- the dispatcher round trip of the custom op is ~10 us, a sixth of the kernel at
+        # BASELINE configs[1] (seq 1024, batch 32)
+        return _mix_impl(V, gate, memory, int(n_fft), int(group_width))
     return _spectral_mix_op(V, gate, memory, int(n_fft), int(group_width))
 
 
@@ -403,6 +410,10 @@ def spectral_mix_anchors(V: torch.Tensor, anchors: torch.Tensor, bias: torch.Ten
     (``spectre.py:526-536``) is evaluated inside the mix kernel's gate staging and the ``(B, NG, F_half)`` gate is never
     materialised.  Arguments as :func:`gate_expand` and :func:`spectral_mix`."""
     _require_cuda(V, "V")
+    needs_grad = torch.is_grad_enabled() and any(
+        t is not None and t.requires_grad for t in (V, anchors, bias, eps, pos_phase, memory))
+    if not needs_grad and not torch.compiler.is_compiling():   # inference: skip the dispatcher (see spectral_mix)
+        return _mix_anchors_impl(V, anchors, bias, eps, pos_phase, memory, int(n_fft), int(group_width), int(G))
     return _spectral_mix_anchors_op(V, anchors, bias, eps, pos_phase, memory, int(n_fft), int(group_width), int(G))
 
 
