@@ -275,7 +275,8 @@ __host__ __device__ constexpr int tmem_slots() { return (PL::kSub || PL::kDit) ?
 #endif
 #ifndef SPX_TMEMX
 #define SPX_TMEMX 0   // 4096-class TMEM kernels, exchanges through tensor memory: bit 0 stage 1 -> middle pass, bit 1 middle pass -> inverse stage 1.
-                      // Correct and 31 % less shared-memory traffic, but no faster (the kernel is not bound there): see DESIGN 3.9
+                      // Correct and 31 % less shared-memory traffic, but no faster (the kernel is not bound there): see DESIGN 3.9.
+                      // (Do not combine with the diagnostic launch flag sched bit 2: the helper would wait for an exchange that mode skips.)
 #endif
 #ifndef SPX_TMEM_COMPUTE_REGS
 #define SPX_TMEM_COMPUTE_REGS 112
