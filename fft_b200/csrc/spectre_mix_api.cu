@@ -124,11 +124,13 @@ std::vector<float2> build_twiddles(const int radix[4]) {
     for (int s = 0; s < ns - 1; ++s) {
         const int R = radix[s], L = N / (P * R);
         // radix-16 stages keep rows q = 1, 2, 3, 4, 8, 12 only (spx::tw_rows): the kernel multiplies the others together
+        // (SPX_TW4 builds: q = 1, 2, 4, 8 for the long tables, spx::tw_rows4)
         static const int rows16[6] = {1, 2, 3, 4, 8, 12};
-        const int nrows = spx::tw_rows(R);
+        static const int rows16_4[4] = {1, 2, 4, 8};
+        const int nrows = spx::tw_rows(R, L);
         for (int j = 0; j < nrows; ++j)
             for (int u = 0; u < L; ++u) {
-                const int q = (R == 16) ? rows16[j] : j + 1;
+                const int q = (R == 16) ? (spx::tw_rows4(R, L) ? rows16_4[j] : rows16[j]) : j + 1;
                 // exponent reduced modulo the period before scaling keeps the angle exact in double
                 const long long period = N / P;
                 const long long e = ((long long)u * q) % period;
@@ -996,15 +998,38 @@ int spectre_mix_fwd_host(const float *v, const float *gate, const float *mem, fl
     HostCtx &h = g_host[dev];
     const size_t fh = n_fft / 2 + 1, ng = C / group_width;
     const size_t row_v = (size_t)N * C * 4, row_o = (size_t)n_io * C * 4, row_g = ng * fh * 8;
-    // batch rows per chunk: ~32 MB of V per chunk -- the call is PCIe-bound, so short chunks (a short pipeline fill before
-    // both copy engines run and a short drain after) matter more than filling every SM with one launch; measured on the
-    // metric shape: 13 MB 1.25e7, 26-52 MB 1.34e7, 104 MB 1.26e7, 208 MB 1.10e7 tokens/s
-    size_t chunk_bytes = 32u << 20;
+    // Chunk schedule.  The call is PCIe-bound (both copy engines busy for ~40 ms at the metric shape), so what matters is (a) a
+    // short pipeline fill before both engines run and a short drain after -- small chunks at the two ends -- and (b) few
+    // copy -> kernel -> copy hand-overs in between -- large chunks in the middle.  Rows per chunk ramp up by doubling from
+    // ~12 MB of V to ~100 MB and back down (1, 2, 4, 8, ..., 8, 4, 2, 1 rows at seq 4096 x d 768).  Measured on the metric
+    // shape (148 rows, profiles/r04b_e2e_probe.txt, r04c_*): uniform 32 MB chunks 43.6 ms, uniform 64 MB 41.9 ms, the same
+    // bytes as two monolithic copies 39.6 ms.  SPECTRE_MIX_HOST_CHUNK_MB (experiment knob) forces uniform chunks of that size.
+    size_t lo_bytes = 12u << 20, hi_bytes = 100u << 20;
+    bool uniform = false;
     if (const char *env = getenv("SPECTRE_MIX_HOST_CHUNK_MB")) {   // experiment knob
         const long mb = strtol(env, nullptr, 10);
-        if (mb > 0 && mb <= 4096) chunk_bytes = (size_t)mb << 20;
+        if (mb > 0 && mb <= 4096) { lo_bytes = hi_bytes = (size_t)mb << 20; uniform = true; }
     }
-    const int rows = (int)std::max<size_t>(1, std::min<size_t>((size_t)B, chunk_bytes / std::max<size_t>(row_v, 1)));
+    if (const char *env = getenv("SPECTRE_MIX_HOST_CHUNK_MAX_MB")) {   // experiment knob: top of the ramp
+        const long mb = strtol(env, nullptr, 10);
+        if (mb > 0 && mb <= 4096) hi_bytes = std::max(lo_bytes, (size_t)mb << 20);
+    }
+    auto rows_for = [&](size_t bytes) { return (int)std::max<size_t>(1, std::min<size_t>((size_t)B, bytes / std::max<size_t>(row_v, 1))); };
+    const int r_lo = rows_for(lo_bytes), r_hi = std::max(r_lo, rows_for(hi_bytes));
+    std::vector<int> sched;   // rows of every chunk, in order
+    {
+        std::vector<int> ramp;
+        int ramp_sum = 0;
+        if (!uniform)
+            for (int r = r_lo; r < r_hi && 2 * (ramp_sum + r) + r_hi <= B; r *= 2) { ramp.push_back(r); ramp_sum += r; }
+        int left = B - 2 * ramp_sum;
+        sched = ramp;
+        const int top = ramp.empty() ? (uniform ? r_hi : r_lo) : r_hi;   // too few rows for a ramp: the small chunk size throughout
+        while (left > 0) { const int r = std::min(top, left); sched.push_back(r); left -= r; }
+        for (size_t i = ramp.size(); i-- > 0;) sched.push_back(ramp[i]);
+    }
+    int rows = 1;   // largest chunk: sizes the per-stream device buffers
+    for (int r : sched) rows = std::max(rows, r);
     const size_t need_v = std::max(row_v, row_o) * rows, need_g = row_g * rows;
     for (int i = 0; i < kHostStreams; ++i) {
         if (!h.s[i] && (e = cudaStreamCreateWithFlags(&h.s[i], cudaStreamNonBlocking)) != cudaSuccess)
@@ -1046,10 +1071,10 @@ int spectre_mix_fwd_host(const float *v, const float *gate, const float *mem, fl
             return cuda_fail(e, "cudaMemcpyAsync(memory)");
         if ((e = cudaStreamSynchronize(h.s[0])) != cudaSuccess) return cuda_fail(e, "sync(memory)");
     }
-    int chunk = 0;
-    for (int b0 = 0; b0 < B; b0 += rows, ++chunk) {
-        const int nb = std::min(rows, B - b0);
-        const int i = chunk % kHostStreams;
+    int b0 = 0;
+    for (size_t chunk = 0; chunk < sched.size(); b0 += sched[chunk], ++chunk) {
+        const int nb = sched[chunk];
+        const int i = (int)(chunk % kHostStreams);
         cudaStream_t s = h.s[i];
         if ((e = cudaMemcpyAsync(h.dv[i], v + (size_t)b0 * N * C, row_v * nb, cudaMemcpyHostToDevice, s)) != cudaSuccess)
             return cuda_fail(e, "H2D V");

@@ -209,7 +209,14 @@ struct Dft<16, V> {
 // Twiddle rows kept per stage.  A radix-16 stage stores only q in {1, 2, 3, 4, 8, 12} (rows 0..5): W^{u (q1 + 4 q0)} =
 // W^{u q1} W^{4 u q0}, so six loads and nine scalar complex products replace fifteen loads -- 40 % of the table, which is
 // what lets the stage-0 table of the 4096-point plan shrink from 30 KB to 12 KB of shared memory.
-__host__ __device__ constexpr int tw_rows(int R) { return R == 16 ? 6 : R - 1; }
+// SPX_TW4 (experiment): a radix-16 stage with a LONG table (L >= 256: stage 0 of the 4096-point plans) stores only q in {1, 2, 4, 8}
+// and forms W^{3u} = W^{u} W^{2u}, W^{12u} = W^{4u} W^{8u} as two more scalar products: 4 KB less shared memory at 4096, which
+// together with the 5 KB that were free is one more ring slot (8 instead of 7) for the TMEM-staged kernel.
+#ifndef SPX_TW4
+#define SPX_TW4 0
+#endif
+__host__ __device__ constexpr bool tw_rows4(int R, int L) { return SPX_TW4 != 0 && R == 16 && L >= 256; }
+__host__ __device__ constexpr int tw_rows(int R, int L) { return R == 16 ? (tw_rows4(R, L) ? 4 : 6) : R - 1; }
 
 // SUBP = 2 (DIT2): the tile's two element columns hold the EVEN and the ODD rows of a transform of length 2 N (same four
 // channels); the two N-point sub-spectra are combined by one decimation-in-time radix-2 butterfly in the middle pass, right
@@ -226,7 +233,7 @@ struct Plan {
     __host__ __device__ static constexpr int P(int s) { return s == 0 ? 1 : (s == 1 ? R0 : (s == 2 ? R0 * R1 : R0 * R1 * R2)); }
     __host__ __device__ static constexpr int L(int s) { return N / (P(s) * R(s)); }
     // twiddles of stage s (s < NS-1): W_{N/P}^{u q}, row j of the stage's table at TWOFF(s) + j L + u (see tw_rows)
-    __host__ __device__ static constexpr int TWOFF(int s) { return s == 0 ? 0 : TWOFF(s - 1) + tw_rows(R(s - 1)) * L(s - 1); }
+    __host__ __device__ static constexpr int TWOFF(int s) { return s == 0 ? 0 : TWOFF(s - 1) + tw_rows(R(s - 1), L(s - 1)) * L(s - 1); }
     static constexpr int TWN = TWOFF(NS - 1);
     static constexpr int NPAD = N + (N >> 4);
     static constexpr int GPAD = (N / 2) + ((N / 2) >> 4) + 1;  // padded gate table length (float2)
@@ -238,7 +245,7 @@ __host__ __device__ constexpr int cmax(int a, int b) { return a > b ? a : b; }
 #ifndef SPX_SUB_TW_SMEM
 #define SPX_SUB_TW_SMEM 1   // sub-transform variant: stage-0 twiddle rows in shared memory (12 KB) at the price of one ring slot
 #endif
-constexpr int kTmemSlotsMax = 7;
+constexpr int kTmemSlotsMax = SPX_TW4 ? 8 : 7;
 constexpr int kTmaBoxRows = 256;
 // TMEM-staged variants: one ring slot = one TMA box of 512 tile elements (8 KB of fp32 rows) but at most 256 rows
 __host__ __device__ constexpr int tmem_box_rows(int ncol) { return 512 / ncol < kTmaBoxRows ? 512 / ncol : kTmaBoxRows; }
@@ -321,10 +328,19 @@ __device__ __forceinline__ void apply_twiddles(Cx<V> (&x)[PL::R(S_)], const floa
     constexpr int R = PL::R(S_), L = PL::L(S_);
     if constexpr (R == 16) {
         float2 a[4], b[4];   // a[q1] = W^{u q1}, b[q0] = W^{4 u q0}
+        if constexpr (tw_rows4(R, L)) {   // rows q = 1, 2, 4, 8; W^{3u} and W^{12u} are products
+            a[1] = tw_get<PL, S_>(tw_s, tw_g, u);
+            a[2] = tw_get<PL, S_>(tw_s, tw_g, L + u);
+            b[1] = tw_get<PL, S_>(tw_s, tw_g, 2 * L + u);
+            b[2] = tw_get<PL, S_>(tw_s, tw_g, 3 * L + u);
+            a[3] = make_float2(fmaf(-a[1].y, a[2].y, a[1].x * a[2].x), fmaf(a[1].x, a[2].y, a[1].y * a[2].x));
+            b[3] = make_float2(fmaf(-b[1].y, b[2].y, b[1].x * b[2].x), fmaf(b[1].x, b[2].y, b[1].y * b[2].x));
+        } else {
 #pragma unroll
-        for (int j = 1; j < 4; ++j) {
-            a[j] = tw_get<PL, S_>(tw_s, tw_g, (j - 1) * L + u);
-            b[j] = tw_get<PL, S_>(tw_s, tw_g, (j + 2) * L + u);
+            for (int j = 1; j < 4; ++j) {
+                a[j] = tw_get<PL, S_>(tw_s, tw_g, (j - 1) * L + u);
+                b[j] = tw_get<PL, S_>(tw_s, tw_g, (j + 2) * L + u);
+            }
         }
         apply_twiddles16(x, a, b);
     } else {

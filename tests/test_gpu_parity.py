@@ -279,6 +279,20 @@ def test_host_entry_point(fb, oracle):
     _check(got2, oracle.mix_flat(V, gate, 1024, 16).numpy())
 
 
+def test_host_entry_ramped_chunk_schedule(fb, dev):
+    """spectre_mix_fwd_host walks the batch in chunks that ramp up from ~12 MB to ~100 MB and back down (short pipeline fill and
+    drain, few hand-overs in between): enough rows for the full ramp, ragged N, checked bit for bit against the device-buffer op
+    on the same rows (which the other tests tie to the oracle)."""
+    torch.manual_seed(77)
+    B, N, n_fft, C, dg = 40, 3900, 4096, 768, 16          # 11.98 MB per row: chunks of 1, 2, 4, 8, 8, 8, 2+..., 4, 2, 1 rows
+    V = torch.randn(B, N, C).pin_memory()
+    gate = torch.randn(B, C // dg, n_fft // 2 + 1, dtype=torch.cfloat).pin_memory()
+    got = fb.spectral_mix_host(V, gate, None, n_fft=n_fft, group_width=dg)
+    want = fb.spectral_mix(V.to(dev), gate.to(dev), n_fft=n_fft, group_width=dg).cpu()
+    assert got.shape == want.shape == (B, N, C)
+    assert torch.equal(got, want)
+
+
 @pytest.mark.parametrize("n_fft,B,C,dg", [(8192, 5, 64, 16), (16384, 4, 64, 16), (8192, 4, 768, 16), (16384, 4, 768, 16)])
 def test_host_entry_point_long_context(n_fft, B, C, dg, fb, oracle):
     """spectre_mix_fwd_host at n_fft = 8192 / 16384 with several chunks in flight (one batch row per chunk at C = 768: the
