@@ -725,6 +725,13 @@ __device__ __forceinline__ auto &pick_ref(A &a, B &b) {
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void helper_bar() { asm volatile("bar.sync 2, 128;" ::: "memory"); }
+// Programmatic dependent launch (the host side sets the launch attribute unless sched bit 6 is set): everything above the wait -- barrier
+// set-up, tensor-memory allocation, the twiddle table (a constant built once per device) -- may run while the previous kernel of
+// the stream is still draining; nothing produced by that kernel is read, and nothing it may still read is written, before the
+// wait.  The trigger right behind it lets the NEXT launch's CTAs take an SM as soon as one of ours exits.  Both are no-ops
+// for a launch without the attribute.
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 // Warp stagger: the four warps that share a scheduler (warp id / 4 = "slot" 0..3) leave a CTA barrier in lock step and would
 // all load, then all compute, then all store.  Holding slot s back by s * clk cycles lets the shared-memory phase of one warp
 // run under the butterflies of another.  code > 0: legacy nanosleep of slots 1 and 3; code < 0: clock spin, |code| % 100000
@@ -1145,6 +1152,8 @@ __global__ void __launch_bounds__(NT + ((TMA_IN && NT >= kSepProducerMinThreads)
         __syncthreads();
         tc_fence_after();
         tmem_base = *tmem_base_s;
+        griddep_wait();
+        griddep_launch();
         if (tid >= NT) {
             asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kTmemHelperRegs));
             const int hl = tid - NT;                              // 0..127 = TMEM lane this helper thread serves
@@ -1355,6 +1364,10 @@ __global__ void __launch_bounds__(NT + ((TMA_IN && NT >= kSepProducerMinThreads)
         } else {
             asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kTmemComputeRegs));
         }
+    }
+    if constexpr (!TMEM_IO) {
+        griddep_wait();
+        griddep_launch();
     }
     if constexpr (TMA_IN && !TMEM_IO) {
         if (tid == (SEP ? NT : 0)) {

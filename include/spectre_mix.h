@@ -219,8 +219,11 @@ int spectre_mix_set_skew_ns(int code);
 /* L2 promotion of the input tensor map (TMA loads): 0 none (default), 1 = 64 B, 2 = 128 B, 3 = 256 B.  For experiments. */
 int spectre_mix_set_l2_promotion(int level);
 
-/* Scheduling flags of the n_fft = 4096 kernel: bit 0 stagger also before the last inverse pass; bit 1 split barrier
- * around the last inverse pass's shared-memory read. */
+/* Scheduling flags (default 3): bit 0 stagger also before the last inverse pass; bit 1 split barrier around the last inverse
+ * pass's shared-memory read (n_fft = 4096 kernel); bit 6 (64) switches programmatic dependent launch OFF.  By default every mix
+ * launch carries cudaLaunchAttributeProgrammaticStreamSerialization: the kernel's set-up (barriers, tensor-memory allocation,
+ * twiddle table) may overlap the tail of the previous kernel of the stream, and it executes griddepcontrol.wait before it reads
+ * or writes any tensor, so stream order of all data accesses is unchanged (also under CUDA-graph capture). */
 int spectre_mix_set_sched(int flags);
 
 /* Debug: device buffer of grid * 5 groups (4 compute thread groups + the helper warpgroup) * 8 tiles * 8 uint64 that receives per-phase %globaltimer stamps

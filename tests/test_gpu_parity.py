@@ -911,6 +911,63 @@ def test_cuda_graph_capture_and_second_stream(fb, dev):
     assert torch.equal(static_out, ref2)
 
 
+@pytest.mark.parametrize("n_fft,B,C", [(256, 16, 64), (1024, 8, 768), (1024, 64, 768), (2048, 32, 768), (4096, 4, 768), (8192, 3, 768),
+                                       (16384, 2, 768)])
+def test_programmatic_dependent_launch_keeps_stream_order(n_fft, B, C, fb, dev):
+    """Every mix launch carries the programmatic-stream-serialization attribute: its set-up may start while the previous kernel of
+    the stream still runs, and griddepcontrol.wait orders all tensor accesses.  A chain of short dependent launches through the C
+    ABI -- each reads what the previous one wrote (RAW) and overwrites what the previous one read (WAR) -- must give the bits
+    of the same chain with the attribute switched off (sched bit 6), eagerly and as a captured CUDA graph."""
+    import ctypes
+    from fft_b200 import _lib
+    lib = _lib.load()
+    dg = 16
+    gen = torch.Generator(device=dev).manual_seed(5 + n_fft)
+    V0 = torch.randn(B, n_fft, C, device=dev, generator=gen)
+    ang = torch.rand(B, C // dg, n_fft // 2 + 1, device=dev, generator=gen) * 6.2831853
+    gate = torch.polar(torch.ones_like(ang), ang).contiguous()       # unit modulus: the chain keeps its scale
+    gate[:, :, 0] = 1.0
+    gate[:, :, -1] = -1.0
+    ws_bytes = lib.spectre_mix_workspace_bytes(0, B, n_fft, n_fft, C, dg)
+    ws = torch.empty(max(int(ws_bytes), 1), dtype=torch.uint8, device=dev)
+
+    def chain(a, b, links=6):
+        st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        for _ in range(links):
+            rc = lib.spectre_mix_fwd_ws(a.data_ptr(), 0, a.stride(0), a.stride(1), gate.data_ptr(), None, C, b.data_ptr(), 0, b.stride(0),
+                                        b.stride(1), B, n_fft, n_fft, C, dg, ws.data_ptr() if ws_bytes else None, int(ws_bytes), st)
+            assert rc == 0, lib.spectre_mix_last_error().decode()
+            a, b = b, a
+        return a
+
+    res = {}
+    try:
+        for name, flags in (("off", 3 | 64), ("on", 3)):
+            lib.spectre_mix_set_sched(flags)
+            a, b = V0.clone(), torch.zeros_like(V0)
+            res[name] = chain(a, b).clone()
+            a.copy_(V0)
+            b.zero_()
+            torch.cuda.synchronize()
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.stream(side):
+                chain(a, b, links=2)                                  # warm-up on the capture stream
+                a.copy_(V0)
+                b.zero_()
+                with torch.cuda.graph(graph, stream=side):
+                    last = chain(a, b)
+            graph.replay()
+            torch.cuda.synchronize()
+            res[name + "_graph"] = last.clone()
+    finally:
+        lib.spectre_mix_set_sched(3)
+    assert torch.isfinite(res["off"]).all() and float(res["off"].abs().max()) > 0.1
+    for k in ("on", "off_graph", "on_graph"):
+        assert torch.equal(res[k], res["off"]), k
+
+
 def test_tmem_variants_race_hunt():
     """Random batch / channel / row counts and dtypes at n_fft = 4096: the TMEM-staged variants under the default schedule
     (helper warpgroup phases, warp stagger, split barrier) agree bit for bit with the plain TMA variant."""
