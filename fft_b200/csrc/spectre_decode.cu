@@ -41,6 +41,10 @@ __global__ void __launch_bounds__(256) decode_kernel(float2 *__restrict__ prefix
                                                      const float *__restrict__ v_old, const float2 *__restrict__ gate,
                                                      float *__restrict__ partial, int n_fft, int d, int group_width, float t_new,
                                                      float t_old, int evict, int pos, float w32) {
+    // programmatic dependent launch: the blocks may become resident while the previous kernel of the stream (the decode gate, the
+    // previous token's reduction) still runs; nothing is read or written before the wait, and the next launch may follow likewise
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const int c = blockIdx.y * blockDim.x + threadIdx.x;
     if (c >= d) return;
     const int F_half = n_fft / 2 + 1;
@@ -94,6 +98,8 @@ __global__ void __launch_bounds__(256) decode_kernel(float2 *__restrict__ prefix
 // out[c] = (sum over frequency chunks, in chunk order) / n_fft -- the fixed order makes the token bit-reproducible run to run
 __global__ void __launch_bounds__(256) decode_reduce_kernel(const float *__restrict__ partial, float *__restrict__ out, int nchunks, int d,
                                                             float nf) {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= d) return;
     float acc = 0.f;
@@ -123,16 +129,29 @@ int launch(int mode, void *prefix, const float *v_new, const float *v_old, const
     float2 *pf = reinterpret_cast<float2 *>(prefix);
     const float2 *g = reinterpret_cast<const float2 *>(gate);
     float *part = reinterpret_cast<float *>(ws);
+    // both launches carry the programmatic-stream-serialization attribute (the kernels wait with griddepcontrol.wait before
+    // they touch memory): a decode step is two dependent 25 MB / 0.4 MB passes, i.e. launch-latency bound
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(threads);
+    cfg.stream = st;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    const float tf = (float)t, jf = (float)j;
+    cudaError_t e;
     switch (mode) {
-        case 1: decode_kernel<1><<<grid, threads, 0, st>>>(pf, v_new, v_old, g, part, n_fft, d, group_width, (float)t, (float)j, evict, pos, w32); break;
-        case 2: decode_kernel<2><<<grid, threads, 0, st>>>(pf, v_new, v_old, g, part, n_fft, d, group_width, (float)t, (float)j, evict, pos, w32); break;
-        default: decode_kernel<3><<<grid, threads, 0, st>>>(pf, v_new, v_old, g, part, n_fft, d, group_width, (float)t, (float)j, evict, pos, w32); break;
+        case 1: e = cudaLaunchKernelEx(&cfg, decode_kernel<1>, pf, v_new, v_old, g, part, n_fft, d, group_width, tf, jf, evict, pos, w32); break;
+        case 2: e = cudaLaunchKernelEx(&cfg, decode_kernel<2>, pf, v_new, v_old, g, part, n_fft, d, group_width, tf, jf, evict, pos, w32); break;
+        default: e = cudaLaunchKernelEx(&cfg, decode_kernel<3>, pf, v_new, v_old, g, part, n_fft, d, group_width, tf, jf, evict, pos, w32); break;
     }
-    cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return spx::cuda_fail(e, "decode kernel launch");
     if (mode & 2) {
-        decode_reduce_kernel<<<(d + 255) / 256, 256, 0, st>>>(part, out, nchunks, d, (float)n_fft);
-        e = cudaGetLastError();
+        cfg.gridDim = dim3((d + 255) / 256);
+        cfg.blockDim = dim3(256);
+        e = cudaLaunchKernelEx(&cfg, decode_reduce_kernel, (const float *)part, out, nchunks, d, (float)n_fft);
         if (e != cudaSuccess) return spx::cuda_fail(e, "decode reduce kernel launch");
     }
     return 0;
