@@ -20,7 +20,10 @@
 
 namespace {
 
-constexpr int kKChunk = 16;  // frequency bins per block
+#ifndef SPX_DECODE_KCHUNK
+#define SPX_DECODE_KCHUNK 16
+#endif
+constexpr int kKChunk = SPX_DECODE_KCHUNK;  // frequency bins per block
 
 // sin / cos of a float32 angle of any size the decode path produces (|theta| up to ~1e5 rad): two-constant Cody-Waite
 // reduction by 2 pi with fused multiply-adds (exact to ~1e-7 rad for |n| < 2^16), then the special-function unit on
@@ -95,16 +98,30 @@ __global__ void __launch_bounds__(256) decode_kernel(float2 *__restrict__ prefix
     if (MODE & 2) partial[(size_t)blockIdx.x * d + c] = acc;
 }
 
-// out[c] = (sum over frequency chunks, in chunk order) / n_fft -- the fixed order makes the token bit-reproducible run to run
-__global__ void __launch_bounds__(256) decode_reduce_kernel(const float *__restrict__ partial, float *__restrict__ out, int nchunks, int d,
-                                                            float nf) {
+// out[c] = (sum over frequency chunks) / n_fft in a FIXED order, so a token is bit-reproducible run to run: a block serves 32
+// channels with 8 slices of threads; slice s adds the partials of chunks s, s + 8, s + 16, ... in order (16 dependent loads per
+// thread at n_fft = 4096 instead of 129), then thread (0, c) adds the 8 slice sums in slice order.
+constexpr int kRedCh = 32, kRedSlices = 8;
+__global__ void __launch_bounds__(kRedCh * kRedSlices) decode_reduce_kernel(const float *__restrict__ partial, float *__restrict__ out,
+                                                                            int nchunks, int d, float nf) {
     asm volatile("griddepcontrol.wait;" ::: "memory");
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= d) return;
+    __shared__ float part_s[kRedSlices][kRedCh];
+    const int cl = threadIdx.x % kRedCh, sl = threadIdx.x / kRedCh;
+    const int c = blockIdx.x * kRedCh + cl;
     float acc = 0.f;
-    for (int i = 0; i < nchunks; ++i) acc += partial[(size_t)i * d + c];
-    out[c] = acc / nf;
+    if (c < d) {
+#pragma unroll 4
+        for (int i = sl; i < nchunks; i += kRedSlices) acc += partial[(size_t)i * d + c];
+    }
+    part_s[sl][cl] = acc;
+    __syncthreads();
+    if (sl == 0 && c < d) {
+        float t = part_s[0][cl];
+#pragma unroll
+        for (int j = 1; j < kRedSlices; ++j) t += part_s[j][cl];
+        out[c] = t / nf;
+    }
 }
 
 int nchunks_of(int n_fft) { return (n_fft / 2 + 1 + kKChunk - 1) / kKChunk; }
@@ -149,8 +166,8 @@ int launch(int mode, void *prefix, const float *v_new, const float *v_old, const
     }
     if (e != cudaSuccess) return spx::cuda_fail(e, "decode kernel launch");
     if (mode & 2) {
-        cfg.gridDim = dim3((d + 255) / 256);
-        cfg.blockDim = dim3(256);
+        cfg.gridDim = dim3((d + kRedCh - 1) / kRedCh);
+        cfg.blockDim = dim3(kRedCh * kRedSlices);
         e = cudaLaunchKernelEx(&cfg, decode_reduce_kernel, (const float *)part, out, nchunks, d, (float)n_fft);
         if (e != cudaSuccess) return spx::cuda_fail(e, "decode reduce kernel launch");
     }

@@ -10,6 +10,9 @@ import time
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from fft_b200 import _lib as _lib0  # noqa: E402
+if os.environ.get("SPX_ALT"):
+    _lib0.LIB_PATH = _lib0.LIB_PATH.replace("libspectre_mix.so", "libspectre_mix_%s.so" % os.environ["SPX_ALT"])
 import fft_b200  # noqa: E402
 from fft_b200 import ops  # noqa: E402
 
