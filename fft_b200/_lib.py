@@ -21,6 +21,7 @@ SYMBOLS = (
     "spectre_mix_last_error",
     "spectre_mix_fwd",
     "spectre_mix_fwd_ws",
+    "spectre_mix_host_release",
     "spectre_mix_fwd_anchors",
     "spectre_mix_anchors_workspace_bytes",
     "spectre_mix_workspace_bytes",
@@ -102,6 +103,8 @@ def load():
         lib.spectre_mix_dgate.argtypes = [vp, vp, i32, i64, i64, i64, i64, vp, i32, i32, i32, i32, i32, vp]
         lib.spectre_mix_fwd_host.restype = i32
         lib.spectre_mix_fwd_host.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32]
+        lib.spectre_mix_host_release.restype = i32
+        lib.spectre_mix_host_release.argtypes = []
         lib.spectre_rfft_fwd.restype = i32
         lib.spectre_rfft_fwd.argtypes = [vp, i32, i64, i64, vp, i32, i32, i32, i32, vp]
         lib.spectre_decode_update.restype = i32

@@ -1094,4 +1094,28 @@ int spectre_mix_fwd_host(const float *v, const float *gate, const float *mem, fl
     return 0;
 }
 
+int spectre_mix_host_release(void) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;   // no device: nothing was ever allocated
+    }
+    std::lock_guard<std::mutex> lock(g_host_mu);
+    auto it = g_host.find(dev);
+    if (it == g_host.end()) return 0;
+    HostCtx &h = it->second;
+    for (int i = 0; i < kHostStreams; ++i) {
+        if (h.s[i]) cudaStreamSynchronize(h.s[i]);
+        cudaFree(h.dv[i]);
+        cudaFree(h.dout[i]);
+        cudaFree(h.dg[i]);
+        cudaFree(h.dws[i]);
+        if (h.s[i]) cudaStreamDestroy(h.s[i]);
+    }
+    cudaFree(h.dmem);
+    g_host.erase(it);
+    cudaGetLastError();
+    return 0;
+}
+
 }  // extern "C"

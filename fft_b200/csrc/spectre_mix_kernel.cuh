@@ -578,10 +578,25 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 // box {channels, rows, 1} of the [B][rows][C] tensor -> dense [rows][channels] in shared memory
+// SPX_L2HINT (experiment): L2 evict-first policy on the tile loads (bit 0) / the result stores (bit 1) -- every byte is touched once
+#ifndef SPX_L2HINT
+#define SPX_L2HINT 0
+#endif
+__device__ __forceinline__ uint64_t l2_evict_first_policy() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
 __device__ __forceinline__ void tma_load_3d(uint32_t dst, const void *tmap, int c, int row, int b, uint32_t bar) {
+#if SPX_L2HINT & 1
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3, %4}], [%5], %6;"
+        ::"r"(dst), "l"(tmap), "r"(c), "r"(row), "r"(b), "r"(bar), "l"(l2_evict_first_policy()) : "memory");
+#else
     asm volatile(
         "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
         ::"r"(dst), "l"(tmap), "r"(c), "r"(row), "r"(b), "r"(bar) : "memory");
+#endif
 }
 __device__ __forceinline__ void tma_prefetch_3d(const void *tmap, int c, int row, int b) {
     asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(tmap), "r"(c), "r"(row), "r"(b)
@@ -593,9 +608,15 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 }
 // dense [rows][channels] in shared memory -> box {channels, rows, 1} of the [B][rows][C] output (clipped at the edges)
 __device__ __forceinline__ void tma_store_3d(const void *tmap, uint32_t src, int c, int row, int b) {
+#if SPX_L2HINT & 2
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group.L2::cache_hint [%0, {%1, %2, %3}], [%4], %5;" ::"l"(tmap), "r"(c),
+                 "r"(row), "r"(b), "r"(src), "l"(l2_evict_first_policy())
+                 : "memory");
+#else
     asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%1, %2, %3}], [%4];" ::"l"(tmap), "r"(c),
                  "r"(row), "r"(b), "r"(src)
                  : "memory");
+#endif
 }
 // rank-4 forms for the DIT2 variant: tensor [B][n][parity][C] (row = 2 n + parity), box {channels, 2, rows, 1}
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const void *tmap, int c, int par, int row, int b, uint32_t bar) {

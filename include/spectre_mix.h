@@ -125,6 +125,11 @@ int spectre_mix_dgate(const void *v, const void *dy, int dtype, int64_t v_stride
 int spectre_mix_fwd_host(const float *v, const float *gate, const float *mem, float *out,
                          int B, int N, int n_fft, int C, int group_width);
 
+/* The host entry keeps its device staging (four streams, each with a V, an out and a gate chunk of up to ~100 MB of V:
+ * ~0.85 GB at seq 4096 x d 768, plus the long-context workspaces) between calls so that a steady caller never allocates.
+ * This frees it for the current device; the next spectre_mix_fwd_host call allocates again.  Returns 0. */
+int spectre_mix_host_release(void);
+
 /* Forward half only: spec[b, k, c] = rfft_{n_fft}(V[b, :, c])[k], k <= n_fft/2.
  * Replaces spectre.py:776-777 (PrefixFFTCache.prefill: pad + rfft along dim 0,
  * B = 1) and is the V_fft of :506.  spec is complex64 [B][n_fft/2+1][C] contiguous. */

@@ -291,6 +291,16 @@ def test_host_entry_ramped_chunk_schedule(fb, dev):
     want = fb.spectral_mix(V.to(dev), gate.to(dev), n_fft=n_fft, group_width=dg).cpu()
     assert got.shape == want.shape == (B, N, C)
     assert torch.equal(got, want)
+    # the staging buffers are kept between calls; releasing them returns the memory and the next call allocates again
+    from fft_b200 import _lib
+    lib = _lib.load()
+    torch.cuda.synchronize()
+    free0 = torch.cuda.mem_get_info()[0]
+    assert lib.spectre_mix_host_release() == 0
+    assert torch.cuda.mem_get_info()[0] - free0 > 300 << 20
+    assert lib.spectre_mix_host_release() == 0                       # idempotent
+    got2 = fb.spectral_mix_host(V[:3], gate[:3], None, n_fft=n_fft, group_width=dg)
+    assert torch.equal(got2, want[:3])
 
 
 @pytest.mark.parametrize("n_fft,B,C,dg", [(8192, 5, 64, 16), (16384, 4, 64, 16), (8192, 4, 768, 16), (16384, 4, 768, 16)])
