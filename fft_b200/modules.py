@@ -256,20 +256,22 @@ def _heads_batchable(mh) -> bool:
                and len(h.gate_mlp) == 3 and h.q_norm.eps == h0.q_norm.eps for h in mh.heads)
 
 
-def multihead_anchors(mh, Q_all: torch.Tensor):
+def multihead_anchors(mh, Q_all: Optional[torch.Tensor], q_pool: Optional[torch.Tensor] = None):
     """spectre.py:511-516 of ALL heads at once (evaluated H times by the loop of :712-713).
 
-    Q_all (B, N, H, d_h).  Pooled descriptor -> per-head LayerNorm -> per-head 2-layer MLP as two batched GEMMs over the
-    stacked head weights.  Returns anchors (B, H*G, Bk) complex64, the stacked modReLU bias (H*G, F_half) and eps (H*G,),
-    and q_pool (B, H*d_h), the concatenation of :718-719.
+    Q_all (B, N, H, d_h), or its mean over the sequence ``q_pool`` (B, H, d_h) when the caller already has it.  Pooled
+    descriptor -> per-head LayerNorm -> per-head 2-layer MLP as two batched GEMMs over the stacked head weights.  Returns
+    anchors (B, H*G, Bk) complex64, the stacked modReLU bias (H*G, F_half) and eps (H*G,), and q_pool (B, H*d_h), the
+    concatenation of :718-719.
     """
     heads, h0 = mh.heads, mh.heads[0]
     H, G, Bk, F_half = len(heads), h0.G, h0.B, h0.F_half
-    Bsz = Q_all.shape[0]
+    Bsz = (Q_all if q_pool is None else q_pool).shape[0]
     if any(type(h.pooling).__name__ == "DCTPooling" for h in heads):
         warnings.warn("DCT pooling unavailable, falling back to mean pooling. "
                       "Consider installing torch_dct or re-tuning hyperparameters.")
-    q_pool = Q_all.mean(dim=1)                                                            # (B, H, d_h)   :511 pooling
+    if q_pool is None:
+        q_pool = Q_all.mean(dim=1)                                                        # (B, H, d_h)   :511 pooling
     qn = F.layer_norm(q_pool, (h0.d,), None, None, h0.q_norm.eps)
     qn = qn * _stacked(mh, "q_norm.weight") + _stacked(mh, "q_norm.bias")                 # :511 q_norm
     hid = torch.einsum("bhi,hoi->bho", qn, _stacked(mh, "gate_mlp.0.weight")) + _stacked(mh, "gate_mlp.0.bias")
@@ -303,13 +305,17 @@ def multihead_forward(mh, x, pos_phase=None, memory_fft=None):
     B, N, d = x.shape
     xh = x.unflatten(-1, (H, d // H))   # any strides, like the torch.chunk of spectre.py:703
     V_all = torch.einsum("bnhi,hoi->bnho", xh, _stacked(mh, "W_v.weight")).reshape(B, N, d)   # head h = channels [h*d_h, (h+1)*d_h)
-    Q_all = torch.einsum("bnhi,hoi->bnho", xh, _stacked(mh, "W_q.weight"))                    # (B, N, H, d_h)
     if x.is_cuda and _heads_batchable(mh):
+        # Every head pools its queries by a plain mean (spectre.py:511 with MeanPool): the mean over the sequence commutes with
+        # the bias-free projection W_q (:502), mean_n(W_q x_n) = W_q mean_n(x_n), so the (B, N, d) query tensor -- whose only
+        # consumer is that mean -- is never formed: one pass over x instead of a projection, a write and a read of (B, N, d).
+        q_mean = torch.einsum("bhi,hoi->bho", x.mean(dim=1).unflatten(-1, (H, d // H)), _stacked(mh, "W_q.weight"))
         # gate generator tail fused into the mix kernel: anchors in, no (B, H*G, F_half) gate tensor
-        anchors, bias, eps, q_pool = multihead_anchors(mh, Q_all)
+        anchors, bias, eps, q_pool = multihead_anchors(mh, None, q_pool=q_mean)
         mixed = spectral_mix_anchors(V_all, anchors, bias, eps, pos_phase, memory_fft, n_fft=h0.n_fft, group_width=h0.d_g, G=h0.G)
         gate_all = None
     else:
+        Q_all = torch.einsum("bnhi,hoi->bnho", xh, _stacked(mh, "W_q.weight"))                # (B, N, H, d_h)
         gates, pools = [], []
         for i, h in enumerate(mh.heads):
             g, qp = head_gate(h, Q_all[:, :, i, :], pos_phase)
