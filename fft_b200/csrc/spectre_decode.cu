@@ -24,6 +24,10 @@ namespace {
 #define SPX_DECODE_KCHUNK 16
 #endif
 constexpr int kKChunk = SPX_DECODE_KCHUNK;  // frequency bins per block
+#ifndef SPX_DECODE_UNROLL
+#define SPX_DECODE_UNROLL 8
+#endif
+constexpr int kUnroll = SPX_DECODE_UNROLL;   // bins in flight per thread
 
 // sin / cos of a float32 angle of any size the decode path produces (|theta| up to ~1e5 rad): two-constant Cody-Waite
 // reduction by 2 pi with fused multiply-adds (exact to ~1e-7 rad for |n| < 2^16), then the special-function unit on
@@ -63,7 +67,7 @@ __global__ void __launch_bounds__(256) decode_kernel(float2 *__restrict__ prefix
     const float posf = (float)pos, nf = (float)n_fft;
     const float nyq_sign = (pos & 1) ? -1.f : 1.f;
     float acc = 0.f;
-#pragma unroll 8
+#pragma unroll kUnroll
     for (int k = k0; k < k1; ++k) {
         float2 X = prefix[(size_t)k * d + c];
         const float kf = (float)k;
