@@ -461,7 +461,7 @@ def main():
         h2d, d2h = int(hV.numel() * 4 + hg.numel() * 8), int(ho.numel() * 4)
         e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                "batch_per_gpu": Be, "steps": args.e2e_steps,
-               "entry": "spectre_mix_fwd_host (C ABI, pinned host buffers, chunked H2D/kernel/D2H on 4 streams)",
+               "entry": "spectre_mix_fwd_host (C ABI, pinned host buffers, ramped chunks of H2D/kernel/D2H on 4 streams)",
                "per_rank_tokens_per_s": [Be * SEQ * args.e2e_steps / float(t[0].item()) for t in per_rank],
                "copy_ceiling": {"what": "the same V and out bytes as plain pinned cudaMemcpyAsync, H2D and D2H at once on two "
                                         "streams, all ranks together, no kernel",
@@ -497,6 +497,8 @@ def main():
                        "parallelism": f"batch-shard x{world} (shard_rows; no data-path collective)",
                        "l2": f"inputs larger than L2: the rank's shard of V is {rows * SEQ * D_MODEL * 4 / 1e9:.1f} GB resident in HBM, "
                              f"every micro-batch reads {min(MB, rows) * SEQ * D_MODEL * 4 / 1e6:.0f} MB of it once per step",
+                       "launch": "programmatic dependent launch: each micro-batch's set-up overlaps the previous launch's tail "
+                                 "(griddepcontrol.wait before any tensor access)",
                        "plan": fft_b200.plan_info(min(MB, rows), SEQ, SEQ, D_MODEL, D_G)},
             "roofline": roofline, "parity_check": parity, "e2e": e2e, "cpu_baseline": cpu, "clocks": clk.summary(),
             "gpu_launches": args.steps * len(micro) * world, "checksum": checksum,
