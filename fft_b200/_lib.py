@@ -22,6 +22,7 @@ SYMBOLS = (
     "spectre_mix_fwd",
     "spectre_mix_fwd_ws",
     "spectre_mix_host_release",
+    "spectre_mix_host_schedule",
     "spectre_mix_fwd_anchors",
     "spectre_mix_anchors_workspace_bytes",
     "spectre_mix_workspace_bytes",
@@ -105,6 +106,8 @@ def load():
         lib.spectre_mix_fwd_host.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32]
         lib.spectre_mix_host_release.restype = i32
         lib.spectre_mix_host_release.argtypes = []
+        lib.spectre_mix_host_schedule.restype = i32
+        lib.spectre_mix_host_schedule.argtypes = [i32, i32, i32, ctypes.POINTER(ctypes.c_int), i32]
         lib.spectre_rfft_fwd.restype = i32
         lib.spectre_rfft_fwd.argtypes = [vp, i32, i64, i64, vp, i32, i32, i32, i32, vp]
         lib.spectre_decode_update.restype = i32

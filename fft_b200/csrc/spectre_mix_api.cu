@@ -980,6 +980,37 @@ struct HostCtx {
 };
 std::mutex g_host_mu;
 std::map<int, HostCtx> g_host;
+// Chunk schedule of the host entry.  The call is PCIe-bound (both copy engines busy for ~40 ms at the metric shape), so what
+// matters is (a) a short pipeline fill before both engines run and a short drain after -- small chunks at the two ends -- and
+// (b) few copy -> kernel -> copy hand-overs in between -- large chunks in the middle.  Rows per chunk ramp up by doubling from
+// ~12 MB of V to ~100 MB and back down (1, 2, 4, 8, ..., 8, 4, 2, 1 rows at seq 4096 x d 768).  Measured on the metric
+// shape (148 rows, profiles/r04b_e2e_probe.txt, r04d_e2e_ab.txt): uniform 32 MB chunks 44.1 ms, uniform 64 MB 42.4 ms, ramped
+// 42.2 ms; the same bytes as two monolithic copies 39.6 ms.  SPECTRE_MIX_HOST_CHUNK_MB (experiment knob) forces uniform chunks
+// of that size, SPECTRE_MIX_HOST_CHUNK_MAX_MB moves the top of the ramp.
+std::vector<int> host_chunk_schedule(int B, size_t row_v) {
+    size_t lo_bytes = 12u << 20, hi_bytes = 100u << 20;
+    bool uniform = false;
+    if (const char *env = getenv("SPECTRE_MIX_HOST_CHUNK_MB")) {
+        const long mb = strtol(env, nullptr, 10);
+        if (mb > 0 && mb <= 4096) { lo_bytes = hi_bytes = (size_t)mb << 20; uniform = true; }
+    }
+    if (const char *env = getenv("SPECTRE_MIX_HOST_CHUNK_MAX_MB")) {
+        const long mb = strtol(env, nullptr, 10);
+        if (mb > 0 && mb <= 4096) hi_bytes = std::max(lo_bytes, (size_t)mb << 20);
+    }
+    auto rows_for = [&](size_t bytes) { return (int)std::max<size_t>(1, std::min<size_t>((size_t)B, bytes / std::max<size_t>(row_v, 1))); };
+    const int r_lo = rows_for(lo_bytes), r_hi = std::max(r_lo, rows_for(hi_bytes));
+    std::vector<int> ramp, sched;
+    long long ramp_sum = 0;
+    if (!uniform)
+        for (long long r = r_lo; r < r_hi && 2 * (ramp_sum + r) + r_hi <= B; r *= 2) { ramp.push_back((int)r); ramp_sum += r; }
+    int left = B - (int)(2 * ramp_sum);
+    sched = ramp;
+    const int top = ramp.empty() ? (uniform ? r_hi : r_lo) : r_hi;   // too few rows for a ramp: the small chunk size throughout
+    while (left > 0) { const int r = std::min(top, left); sched.push_back(r); left -= r; }
+    for (size_t i = ramp.size(); i-- > 0;) sched.push_back(ramp[i]);
+    return sched;
+}
 }  // namespace
 
 int spectre_mix_fwd_host(const float *v, const float *gate, const float *mem, float *out, int B, int N, int n_fft,
@@ -998,36 +1029,7 @@ int spectre_mix_fwd_host(const float *v, const float *gate, const float *mem, fl
     HostCtx &h = g_host[dev];
     const size_t fh = n_fft / 2 + 1, ng = C / group_width;
     const size_t row_v = (size_t)N * C * 4, row_o = (size_t)n_io * C * 4, row_g = ng * fh * 8;
-    // Chunk schedule.  The call is PCIe-bound (both copy engines busy for ~40 ms at the metric shape), so what matters is (a) a
-    // short pipeline fill before both engines run and a short drain after -- small chunks at the two ends -- and (b) few
-    // copy -> kernel -> copy hand-overs in between -- large chunks in the middle.  Rows per chunk ramp up by doubling from
-    // ~12 MB of V to ~100 MB and back down (1, 2, 4, 8, ..., 8, 4, 2, 1 rows at seq 4096 x d 768).  Measured on the metric
-    // shape (148 rows, profiles/r04b_e2e_probe.txt, r04c_*): uniform 32 MB chunks 43.6 ms, uniform 64 MB 41.9 ms, the same
-    // bytes as two monolithic copies 39.6 ms.  SPECTRE_MIX_HOST_CHUNK_MB (experiment knob) forces uniform chunks of that size.
-    size_t lo_bytes = 12u << 20, hi_bytes = 100u << 20;
-    bool uniform = false;
-    if (const char *env = getenv("SPECTRE_MIX_HOST_CHUNK_MB")) {   // experiment knob
-        const long mb = strtol(env, nullptr, 10);
-        if (mb > 0 && mb <= 4096) { lo_bytes = hi_bytes = (size_t)mb << 20; uniform = true; }
-    }
-    if (const char *env = getenv("SPECTRE_MIX_HOST_CHUNK_MAX_MB")) {   // experiment knob: top of the ramp
-        const long mb = strtol(env, nullptr, 10);
-        if (mb > 0 && mb <= 4096) hi_bytes = std::max(lo_bytes, (size_t)mb << 20);
-    }
-    auto rows_for = [&](size_t bytes) { return (int)std::max<size_t>(1, std::min<size_t>((size_t)B, bytes / std::max<size_t>(row_v, 1))); };
-    const int r_lo = rows_for(lo_bytes), r_hi = std::max(r_lo, rows_for(hi_bytes));
-    std::vector<int> sched;   // rows of every chunk, in order
-    {
-        std::vector<int> ramp;
-        int ramp_sum = 0;
-        if (!uniform)
-            for (int r = r_lo; r < r_hi && 2 * (ramp_sum + r) + r_hi <= B; r *= 2) { ramp.push_back(r); ramp_sum += r; }
-        int left = B - 2 * ramp_sum;
-        sched = ramp;
-        const int top = ramp.empty() ? (uniform ? r_hi : r_lo) : r_hi;   // too few rows for a ramp: the small chunk size throughout
-        while (left > 0) { const int r = std::min(top, left); sched.push_back(r); left -= r; }
-        for (size_t i = ramp.size(); i-- > 0;) sched.push_back(ramp[i]);
-    }
+    const std::vector<int> sched = host_chunk_schedule(B, row_v);   // rows of every chunk, in order
     int rows = 1;   // largest chunk: sizes the per-stream device buffers
     for (int r : sched) rows = std::max(rows, r);
     const size_t need_v = std::max(row_v, row_o) * rows, need_g = row_g * rows;
@@ -1092,6 +1094,14 @@ int spectre_mix_fwd_host(const float *v, const float *gate, const float *mem, fl
     for (int i = 0; i < kHostStreams; ++i)
         if ((e = cudaStreamSynchronize(h.s[i])) != cudaSuccess) return cuda_fail(e, "stream sync");
     return 0;
+}
+
+int spectre_mix_host_schedule(int B, int N, int C, int *rows_out, int cap) {
+    if (B < 0 || N <= 0 || C <= 0 || (!rows_out && cap > 0)) return -1;
+    if (B == 0) return 0;
+    const std::vector<int> sched = host_chunk_schedule(B, (size_t)N * C * 4);
+    for (int i = 0; i < (int)sched.size() && i < cap; ++i) rows_out[i] = sched[i];
+    return (int)sched.size();
 }
 
 int spectre_mix_host_release(void) {

@@ -130,6 +130,11 @@ int spectre_mix_fwd_host(const float *v, const float *gate, const float *mem, fl
  * This frees it for the current device; the next spectre_mix_fwd_host call allocates again.  Returns 0. */
 int spectre_mix_host_release(void);
 
+/* Introspection (no GPU needed): the batch-chunk schedule spectre_mix_fwd_host uses for B rows of N x C fp32 -- rows per chunk,
+ * ramping up by doubling from ~12 MB of V to ~100 MB and back down (short pipeline fill and drain, few hand-overs in between).
+ * Writes at most `cap` entries to rows_out and returns the number of chunks (-1 on bad arguments). */
+int spectre_mix_host_schedule(int B, int N, int C, int *rows_out, int cap);
+
 /* Forward half only: spec[b, k, c] = rfft_{n_fft}(V[b, :, c])[k], k <= n_fft/2.
  * Replaces spectre.py:776-777 (PrefixFFTCache.prefill: pad + rfft along dim 0,
  * B = 1) and is the V_fft of :506.  spec is complex64 [B][n_fft/2+1][C] contiguous. */

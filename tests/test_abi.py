@@ -55,6 +55,42 @@ def test_argument_validation_needs_no_gpu():
     assert rc == 0
 
 
+def test_host_entry_chunk_schedule(monkeypatch):
+    """Host logic of spectre_mix_fwd_host (no GPU): the batch is walked in chunks whose row counts ramp up by doubling from
+    ~12 MB of V to ~100 MB and back down; every row is covered exactly once whatever the sizes."""
+    import ctypes
+    from fft_b200 import _lib
+    lib = _lib.load()
+    monkeypatch.delenv("SPECTRE_MIX_HOST_CHUNK_MB", raising=False)
+    monkeypatch.delenv("SPECTRE_MIX_HOST_CHUNK_MAX_MB", raising=False)
+
+    def sched(B, N, C):
+        buf = (ctypes.c_int * 4096)()
+        n = lib.spectre_mix_host_schedule(B, N, C, buf, 4096)
+        assert 0 <= n <= 4096
+        return list(buf[:n])
+
+    s = sched(148, 4096, 768)                      # the bench's e2e step: 12.6 MB per row
+    assert sum(s) == 148 and s[:3] == [1, 2, 4] and s[-3:] == [4, 2, 1] and max(s) == 8 and all(r >= 1 for r in s)
+    mid = s[3:-3]
+    assert all(r == 8 for r in mid[:-1]) and 1 <= mid[-1] <= 8
+    assert sched(3, 4096, 768) == [1, 1, 1]        # too few rows for a ramp: the small chunk size throughout
+    assert sched(0, 4096, 768) == []
+    assert sched(5, 16384, 768) == [1, 2, 1, 1]        # 50 MB rows: the ramp is 1 -> 2 rows, the remainder chunk before the way down
+    for (B, N, C) in [(1, 32, 4), (7, 100, 12), (600, 1024, 64), (8192, 4096, 768), (33, 20000, 8), (1000, 128, 64)]:
+        s = sched(B, N, C)
+        assert sum(s) == B and all(r >= 1 for r in s), (B, N, C, s)
+        row = N * C * 4
+        assert max(s) * row <= max(100 << 20, row)       # no chunk above ~100 MB unless a single row is
+        half = len(s) // 2
+        assert s[:half] == sorted(s[:half]) or len(set(s)) <= 2      # rising front ...
+        assert s[-3:] == sorted(s[-3:], reverse=True) or len(s) < 3   # ... falling tail
+    monkeypatch.setenv("SPECTRE_MIX_HOST_CHUNK_MB", "32")           # experiment knob: uniform chunks
+    s = sched(148, 4096, 768)
+    assert sum(s) == 148 and set(s[:-1]) == {2}
+    assert lib.spectre_mix_host_schedule(-1, 4096, 768, None, 0) == -1
+
+
 def test_no_cpu_fallback():
     """The product path must fail loudly on CPU tensors instead of computing on the host."""
     import torch
