@@ -770,6 +770,14 @@ int mix_fwd_impl(const void *v, int v_dtype, int64_t v_stride_b, int64_t v_strid
                make_v_tensor_map(&tmap_out, out, out_dtype, out_stride_b, out_stride_n, B, n_io, C,
                                  tmem ? c.k->tmem_box_rows : c.k->out_box_rows, tile_ch);
     if (!tma) tmem = false;
+    // The narrow n_fft = 1024 variant (TMA landing in the working buffer, two CTAs per SM: what short launches such as BASELINE
+    // configs[1] run) gains 1-2 % from the warp stagger the tensor-memory variants use, with a 500-cycle step
+    // (profiles/r04w_ab_stagger_1024.txt: batch 8 / 16 / 24 / 32 / 40: +0.4 / +1.8 / +1.4 / +1.8 / -0.2 %).  Only with the knobs at
+    // their defaults, so experiments keep full control.
+    if (tma && !tmem && n_fft == 1024 && p.skew_ns == -350 && !(p.sched & 64)) {
+        p.sched |= 64;
+        p.skew_ns = -500;
+    }
     const int occ = std::max(1, occupancy_of(*st, c, mem != nullptr, tma, tmem));
     // paired tile order (TMEM variant): the two channel tiles of one gate group back to back, gate row staged once for both
     p.pair_tiles = (tmem && (p.sched & 16) && c.gate_tables == 1 && c.tiles_per_row % 2 == 0 && group_width % (2 * tile_ch) == 0) ? 1 : 0;

@@ -746,7 +746,7 @@ __device__ __forceinline__ auto &pick_ref(A &a, B &b) {
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void helper_bar() { asm volatile("bar.sync 2, 128;" ::: "memory"); }
-// Programmatic dependent launch (the host side sets the launch attribute unless sched bit 6 is set): everything above the wait -- barrier
+// Programmatic dependent launch (the host side sets the launch attribute unless sched bit 7 is set): everything above the wait -- barrier
 // set-up, tensor-memory allocation, the twiddle table (a constant built once per device) -- may run while the previous kernel of
 // the stream is still draining; nothing produced by that kernel is read, and nothing it may still read is written, before the
 // wait.  The trigger right behind it lets the NEXT launch's CTAs take an SM as soon as one of ours exits.  Both are no-ops

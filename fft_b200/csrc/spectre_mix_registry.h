@@ -81,7 +81,7 @@ struct Launcher {
         alignas(64) CUtensorMap tm, tmo;
         if (tmap) { tm = *tmap; tmo = *tmap_out; } else { memset(&tm, 0, sizeof(tm)); memset(&tmo, 0, sizeof(tmo)); }
         void *args[] = {&pc, &tm, &tmo};
-        // Programmatic dependent launch (sched bit 6 switches it OFF): the kernel's set-up may overlap the tail of the previous
+        // Programmatic dependent launch (sched bit 7 switches it OFF): the kernel's set-up may overlap the tail of the previous
         // kernel of the stream; it waits with griddepcontrol.wait before it touches any tensor (griddep_wait in the kernel header)
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(grid);
@@ -92,7 +92,7 @@ struct Launcher {
         attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         attr[0].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = attr;
-        cfg.numAttrs = (p.sched & 64) ? 0 : 1;
+        cfg.numAttrs = (p.sched & 128) ? 0 : 1;
         return cudaLaunchKernelExC(&cfg, f, args);
     }
     static cudaError_t launch_rfft(const MixParams &p, int grid, cudaStream_t st) {

@@ -230,7 +230,7 @@ int spectre_mix_set_skew_ns(int code);
 int spectre_mix_set_l2_promotion(int level);
 
 /* Scheduling flags (default 3): bit 0 stagger also before the last inverse pass; bit 1 split barrier around the last inverse
- * pass's shared-memory read (n_fft = 4096 kernel); bit 6 (64) switches programmatic dependent launch OFF.  By default every mix
+ * pass's shared-memory read (n_fft = 4096 kernel); bit 6 (64) applies the warp stagger to the variants without tensor-memory staging too (experiments); bit 7 (128) switches programmatic dependent launch OFF.  By default every mix
  * launch carries cudaLaunchAttributeProgrammaticStreamSerialization: the kernel's set-up (barriers, tensor-memory allocation,
  * twiddle table) may overlap the tail of the previous kernel of the stream, and it executes griddepcontrol.wait before it reads
  * or writes any tensor, so stream order of all data accesses is unchanged (also under CUDA-graph capture). */

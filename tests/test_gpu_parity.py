@@ -927,7 +927,7 @@ def test_programmatic_dependent_launch_keeps_stream_order(n_fft, B, C, fb, dev):
     """Every mix launch carries the programmatic-stream-serialization attribute: its set-up may start while the previous kernel of
     the stream still runs, and griddepcontrol.wait orders all tensor accesses.  A chain of short dependent launches through the C
     ABI -- each reads what the previous one wrote (RAW) and overwrites what the previous one read (WAR) -- must give the bits
-    of the same chain with the attribute switched off (sched bit 6), eagerly and as a captured CUDA graph."""
+    of the same chain with the attribute switched off (sched bit 7), eagerly and as a captured CUDA graph."""
     import ctypes
     from fft_b200 import _lib
     lib = _lib.load()
@@ -952,7 +952,7 @@ def test_programmatic_dependent_launch_keeps_stream_order(n_fft, B, C, fb, dev):
 
     res = {}
     try:
-        for name, flags in (("off", 3 | 64), ("on", 3)):
+        for name, flags in (("off", 3 | 128), ("on", 3)):
             lib.spectre_mix_set_sched(flags)
             a, b = V0.clone(), torch.zeros_like(V0)
             res[name] = chain(a, b).clone()
